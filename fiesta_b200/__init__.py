@@ -1,0 +1,246 @@
+"""fiesta_b200 -- B200-native (sm_100a) implementation of FIESTA's incremental ESDF hot path.
+
+The product is the C-ABI shared library `fiesta_b200/lib/libfiesta_b200.so` (declared in include/fiesta_b200.h,
+built from fiesta_b200/csrc/*.cu by `fiesta_b200.build.build()`); C++ callers use the drop-in facade
+include/fiesta_b200/ESDFMap.h.  This module is only the ctypes binding that tests/ and bench.py drive it with:
+`ESDFMap` mirrors the reference class's public surface (/root/reference/include/ESDFMap.h:111-164) method for method.
+
+There is no CPU fallback: importing works anywhere, but creating a map without the compiled library or without an
+sm_100 GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfiesta_b200.so")
+
+UNDEFINED = -10000
+INFINITY = 10000
+
+D3 = C.c_double * 3
+I3 = C.c_int * 3
+
+
+class Config(C.Structure):
+    _fields_ = [("origin", C.c_double * 3), ("resolution", C.c_double), ("map_size", C.c_double * 3),
+                ("device", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+class RaycastParams(C.Structure):
+    _fields_ = [("min_ray_length", C.c_double), ("max_ray_length", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in (
+        "occupancy_updates", "inserts", "deletes", "voxels_changed", "voxels_reset", "tile_visits", "generations",
+        "rays_cast", "rays_dropped", "ray_voxels", "raycast_rounds", "touched_voxels", "kernel_launches")] + [
+        (n, C.c_float) for n in ("ms_raycast", "ms_update_occupancy", "ms_update_esdf", "ms_esdf_delete_scan",
+                                 "ms_esdf_wavefront")] + [("reserved_f", C.c_float * 3)]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved_f"}
+
+
+# every symbol include/fiesta_b200.h declares
+SYMBOLS = [
+    "fiesta_create", "fiesta_destroy", "fiesta_last_error", "fiesta_set_parameters", "fiesta_grid_total_size",
+    "fiesta_grid_size", "fiesta_set_occupancy_pos", "fiesta_set_occupancy_vox", "fiesta_set_occupancy_batch_pos",
+    "fiesta_set_occupancy_batch_vox", "fiesta_raycast_frame", "fiesta_raycast_frame_device", "fiesta_check_update",
+    "fiesta_update_occupancy", "fiesta_update_esdf", "fiesta_set_update_range", "fiesta_set_original_range",
+    "fiesta_get_distance_pos", "fiesta_get_distance_vox", "fiesta_get_occupancy_pos", "fiesta_get_occupancy_vox",
+    "fiesta_get_dist_grad_trilinear", "fiesta_get_distance_batch_pos", "fiesta_get_dist_grad_trilinear_batch",
+    "fiesta_export_distance", "fiesta_export_closest_obstacle", "fiesta_export_occupancy", "fiesta_export_counters",
+    "fiesta_get_stats", "fiesta_synchronize",
+]
+
+_lib = None
+
+
+class FiestaError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen the product library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FiestaError("%s is missing: run `python -m fiesta_b200.build` (nvcc, sm_100a). There is no CPU "
+                              "fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.fiesta_last_error.restype = C.c_char_p
+        for n in ("fiesta_get_distance_pos", "fiesta_get_distance_vox", "fiesta_get_dist_grad_trilinear"):
+            getattr(L, n).restype = C.c_double
+        L.fiesta_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+        L.fiesta_destroy.argtypes = [C.c_void_p]
+        L.fiesta_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class ESDFMap:
+    """Mirror of fiesta::ESDFMap (ESDFMap.h:111-164); every method forwards 1:1 to the C ABI."""
+
+    def __init__(self, origin, resolution, map_size, device=0):
+        self._L = load_library()
+        cfg = Config()
+        cfg.origin = D3(*origin)
+        cfg.resolution = float(resolution)
+        cfg.map_size = D3(*map_size)
+        cfg.device = int(device)
+        h = C.c_void_p()
+        rc = self._L.fiesta_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise FiestaError("fiesta_create failed (%d): %s" % (rc, self._L.fiesta_last_error().decode()))
+        self._h = h
+        self.grid_total_size_ = int(self._L.fiesta_grid_total_size(self._h))
+        g = I3()
+        self._L.fiesta_grid_size(self._h, g)
+        self.grid_size = tuple(int(x) for x in g)
+        self.resolution = float(resolution)
+        self.device = int(device)
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise FiestaError("%s failed (%d): %s" % (what, rc, self._L.fiesta_last_error().decode()))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.fiesta_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- ESDFMap public surface ---
+    def SetParameters(self, p_hit, p_miss, p_min, p_max, p_occ):
+        self._ck(self._L.fiesta_set_parameters(self._h, *(C.c_double(x) for x in (p_hit, p_miss, p_min, p_max, p_occ))),
+                 "SetParameters")
+
+    def SetOccupancy(self, p, occ):
+        if all(isinstance(x, (int, np.integer)) for x in p):
+            return int(self._L.fiesta_set_occupancy_vox(self._h, I3(*[int(x) for x in p]), int(occ)))
+        return int(self._L.fiesta_set_occupancy_pos(self._h, D3(*[float(x) for x in p]), int(occ)))
+
+    def SetOccupancyBatchVox(self, vox, occ):
+        vox = np.ascontiguousarray(vox, dtype=np.int32).reshape(-1, 3)
+        occ = np.ascontiguousarray(occ, dtype=np.uint8)
+        out = np.empty(len(vox), np.int32)
+        self._ck(self._L.fiesta_set_occupancy_batch_vox(self._h, vox.ctypes, occ.ctypes, C.c_int64(len(vox)), out.ctypes),
+                 "SetOccupancy batch")
+        return out
+
+    def SetOccupancyBatchPos(self, pos, occ):
+        pos = _f64(pos).reshape(-1, 3)
+        occ = np.ascontiguousarray(occ, dtype=np.uint8)
+        out = np.empty(len(pos), np.int32)
+        self._ck(self._L.fiesta_set_occupancy_batch_pos(self._h, pos.ctypes, occ.ctypes, C.c_int64(len(pos)), out.ctypes),
+                 "SetOccupancy batch")
+        return out
+
+    def CheckUpdate(self):
+        return bool(self._L.fiesta_check_update(self._h))
+
+    def UpdateOccupancy(self, global_map=True):
+        rc = self._L.fiesta_update_occupancy(self._h, int(bool(global_map)))
+        if rc < 0:
+            raise FiestaError("UpdateOccupancy failed (%d): %s" % (rc, self._L.fiesta_last_error().decode()))
+        return bool(rc)
+
+    def UpdateESDF(self):
+        self._ck(self._L.fiesta_update_esdf(self._h), "UpdateESDF")
+
+    def SetUpdateRange(self, min_pos, max_pos, new_vec=True):
+        self._ck(self._L.fiesta_set_update_range(self._h, D3(*min_pos), D3(*max_pos), int(bool(new_vec))), "SetUpdateRange")
+
+    def SetOriginalRange(self):
+        self._ck(self._L.fiesta_set_original_range(self._h), "SetOriginalRange")
+
+    def GetDistance(self, p):
+        if all(isinstance(x, (int, np.integer)) for x in p):
+            return float(self._L.fiesta_get_distance_vox(self._h, I3(*[int(x) for x in p])))
+        return float(self._L.fiesta_get_distance_pos(self._h, D3(*[float(x) for x in p])))
+
+    def GetOccupancy(self, p):
+        if all(isinstance(x, (int, np.integer)) for x in p):
+            return int(self._L.fiesta_get_occupancy_vox(self._h, I3(*[int(x) for x in p])))
+        return int(self._L.fiesta_get_occupancy_pos(self._h, D3(*[float(x) for x in p])))
+
+    def GetDistWithGradTrilinear(self, pos):
+        g = D3()
+        d = float(self._L.fiesta_get_dist_grad_trilinear(self._h, D3(*[float(x) for x in pos]), g))
+        return d, np.array(list(g))
+
+    def GetDistanceBatch(self, pos):
+        pos = _f64(pos).reshape(-1, 3)
+        out = np.empty(len(pos))
+        self._ck(self._L.fiesta_get_distance_batch_pos(self._h, pos.ctypes, C.c_int64(len(pos)), out.ctypes), "GetDistance batch")
+        return out
+
+    def GetDistWithGradTrilinearBatch(self, pos):
+        pos = _f64(pos).reshape(-1, 3)
+        d = np.empty(len(pos))
+        g = np.empty((len(pos), 3))
+        self._ck(self._L.fiesta_get_dist_grad_trilinear_batch(self._h, pos.ctypes, C.c_int64(len(pos)), d.ctypes, g.ctypes),
+                 "GetDistWithGradTrilinear batch")
+        return d, g
+
+    # --- Fiesta::RaycastMultithread (Fiesta.h:281-303), serial semantics ---
+    def RaycastFrame(self, xyz, T, min_ray_length, max_ray_length):
+        """xyz: (n,3) float32 host array, or an integer device pointer paired with `n` as a tuple (ptr, n)."""
+        p = RaycastParams(float(min_ray_length), float(max_ray_length))
+        T = _f64(T).reshape(16)
+        if isinstance(xyz, tuple):
+            ptr, n = xyz
+            self._ck(self._L.fiesta_raycast_frame_device(self._h, C.c_void_p(int(ptr)), C.c_int64(int(n)), T.ctypes, C.byref(p)),
+                     "RaycastFrame(device)")
+        else:
+            xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+            self._ck(self._L.fiesta_raycast_frame(self._h, xyz.ctypes, C.c_int64(len(xyz)), T.ctypes, C.byref(p)), "RaycastFrame")
+        return self.stats()["rays_cast"]
+
+    def RaycastFramePtr(self, host_ptr, n, T, min_ray_length, max_ray_length):
+        """Same, from a raw HOST pointer (e.g. a pinned torch tensor's data_ptr())."""
+        p = RaycastParams(float(min_ray_length), float(max_ray_length))
+        T = _f64(T).reshape(16)
+        self._ck(self._L.fiesta_raycast_frame(self._h, C.c_void_p(int(host_ptr)), C.c_int64(int(n)), T.ctypes, C.byref(p)),
+                 "RaycastFrame")
+
+    # --- state dumps / stats ---
+    def export_distance(self):
+        out = np.empty(self.grid_total_size_)
+        self._ck(self._L.fiesta_export_distance(self._h, out.ctypes), "export_distance")
+        return out
+
+    def export_occupancy(self):
+        out = np.empty(self.grid_total_size_)
+        self._ck(self._L.fiesta_export_occupancy(self._h, out.ctypes), "export_occupancy")
+        return out
+
+    def export_closest_obstacle(self):
+        out = np.empty((self.grid_total_size_, 3), np.int32)
+        self._ck(self._L.fiesta_export_closest_obstacle(self._h, out.ctypes), "export_closest_obstacle")
+        return out
+
+    def export_counters(self):
+        hit = np.empty(self.grid_total_size_, np.int32)
+        tot = np.empty(self.grid_total_size_, np.int32)
+        self._ck(self._L.fiesta_export_counters(self._h, hit.ctypes, tot.ctypes), "export_counters")
+        return hit, tot
+
+    def stats(self):
+        s = Stats()
+        self._ck(self._L.fiesta_get_stats(self._h, C.byref(s)), "get_stats")
+        return s.asdict()
+
+    def synchronize(self):
+        self._ck(self._L.fiesta_synchronize(self._h), "synchronize")

@@ -1,0 +1,313 @@
+// fiesta_b200 -- incremental ESDF update kernels (replaces ESDFMap::UpdateESDF, /root/reference/src/ESDFMap.cpp:273-398).
+//
+// E1 insert seeds   (ESDFMap.cpp:278-291)  k_seed_inserts : record := {0, self}, activate the tiles within reach.
+// E2 delete         (ESDFMap.cpp:292-337)  k_delete_scan  : the per-obstacle doubly linked lists (ESDFMap.cpp:24-42) are
+//                   gone; dependants of deleted obstacles are found by ONE streaming scan of the closest-obstacle array
+//                   (128-bit loads) against the L2-resident Exist() bitmap, reset, and their tiles activated; the pull
+//                   relaxation below re-seeds them from valid neighbours.
+// E3 wavefront      (ESDFMap.cpp:338-392)  k_wavefront    : persistent cooperative kernel over a device work-list of
+//                   active 8^3 tiles.  Each tile (+2-voxel halo, because dirs_ contains the +-2 axis steps,
+//                   parameters.h:66-68) is staged into shared memory with ONE TMA box load (cp.async.bulk.tensor.3d;
+//                   out-of-grid voxels are zero-filled = "never observed" = barrier), relaxed to a local fixpoint with the
+//                   reference's 24-neighbourhood, strict-improvement rule and unknown-voxel barriers, written to a staging
+//                   grid if it changed, and after a grid-wide barrier committed and its neighbours activated for the next
+//                   generation.  Reads inside a generation only see the previous generation (Jacobi), so the result is
+//                   deterministic and independent of the tile schedule.
+// Frontier semantics: the reference only touches voxels a wave actually reaches -- an observed voxel whose distance is
+// still +10000 stays so until a popped neighbour pushes to it (ESDFMap.cpp:375-391) or it is popped itself and pulls
+// (:349-367).  Bit 31 of a record (FB_FRESH) marks "changed in the previous generation / local iteration" = "is in the
+// update queue": a voxel takes candidates from FRESH neighbours (their push) and, when FRESH itself, from all neighbours
+// (its own pull).  Nothing else is relaxed, so unreached voxels stay unreached exactly like in the reference.
+// Tie-break: the reference keeps the first arrival in FIFO order (ESDFMap.cpp:357,382); a parallel wave has no such
+// order, so exact distance ties go to the smallest packed obstacle coordinate (x, then y, then z).
+#include <cooperative_groups.h>
+#include <stdio.h>
+#include "fb_common.cuh"
+
+namespace cg = cooperative_groups;
+
+__device__ __forceinline__ unsigned ld_cg_u32(const unsigned *p) { return __ldcg(p); }
+
+// Queue tile t for the generation identified by `stamp` (dedupe through tile_flag).
+__device__ __forceinline__ void fb_activate(const FbEsdfArgs &a, unsigned t, unsigned stamp, int which) {
+  if (atomicExch(&a.tile_flag[t], stamp) != stamp) {
+    unsigned slot = atomicAdd(&a.ctr->n_list[which], 1u);
+    a.list[which][slot] = t;
+  }
+}
+
+// ---------------------------------------------------------------- E1
+__global__ void k_seed_inserts(FbGeom g, FbEsdfArgs a, const uint32_t *ins, unsigned n) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned ii = ins[i];
+  if (!(a.occ[ii] > a.l_occ)) return;                       // `if (Exist(idx))`, ESDFMap.cpp:282
+  int z = ii % g.pz, y = (ii / g.pz) % g.gy, x = ii / (g.pz * g.gy);
+  a.cobs[ii] = fb_pack(x, y, z) | FB_FRESH;                 // closest_obstacle_ = self, distance_ = 0, update_queue_.push
+  const unsigned stamp = a.ctr->gen_stamp;
+  int tx0 = max(x - 2, 0) >> 3, tx1 = min(x + 2, g.gx - 1) >> 3;
+  int ty0 = max(y - 2, 0) >> 3, ty1 = min(y + 2, g.gy - 1) >> 3;
+  int tz0 = max(z - 2, 0) >> 3, tz1 = min(z + 2, g.gz - 1) >> 3;
+  for (int tx = tx0; tx <= tx1; ++tx)
+    for (int ty = ty0; ty <= ty1; ++ty)
+      for (int tz = tz0; tz <= tz1; ++tz) fb_activate(a, (unsigned)((tx * g.ty + ty) * g.tz + tz), stamp, 0);
+}
+
+// ---------------------------------------------------------------- E2
+// One thread handles 4 consecutive voxels (one 128-bit load).  ptotal is a multiple of 4 because pz is.
+__global__ void k_delete_scan(FbGeom g, FbEsdfArgs a) {
+  const long long nvec = g.ptotal >> 2;
+  const unsigned stamp = a.ctr->gen_stamp;
+  unsigned local_reset = 0;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
+    uint4 q = reinterpret_cast<const uint4 *>(a.cobs)[v];
+    uint32_t c[4] = {q.x, q.y, q.z, q.w};
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if ((c[k] & FB_CODE_MASK) >= 2u) {
+        int ox, oy, oz;
+        fb_unpack(c[k], ox, oy, oz);
+        long long oi = fb_ii(g, ox, oy, oz);
+        if (!((__ldg(&a.occbits[oi >> 5]) >> (oi & 31)) & 1u)) { c[k] = FB_INF | FB_FRESH; any = true; ++local_reset; }  // !Exist(cobs)
+      }
+    }
+    if (any) {
+      reinterpret_cast<uint4 *>(a.cobs)[v] = make_uint4(c[0], c[1], c[2], c[3]);
+      long long ii = v << 2;                                // the 4 voxels share (x, y) and lie in at most 1 tile (z % 4 == 0)
+      int z = (int)(ii % g.pz), y = (int)((ii / g.pz) % g.gy), x = (int)(ii / ((long long)g.pz * g.gy));
+      fb_activate(a, (unsigned)(((x >> 3) * g.ty + (y >> 3)) * g.tz + (z >> 3)), stamp, 0);
+    }
+  }
+  if (local_reset) atomicAdd(&a.ctr->voxels_reset, (unsigned long long)local_reset);
+}
+
+// ---------------------------------------------------------------- E3
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "FB_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra FB_DONE_%=;\n"
+      "bra FB_WAIT_%=;\n"
+      "FB_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// TMA: one 12x12x12 u32 box (z fastest) -> shared memory, completion signalled on `bar`.
+__device__ __forceinline__ void tma_load_box(void *dst, const CUtensorMap *tmap, int cz, int cy, int cx, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"((unsigned long long)tmap), "r"(cz), "r"(cy), "r"(cx), "r"(smem_u32(bar))
+      : "memory");
+}
+
+#define WF_THREADS 512
+
+__global__ void __launch_bounds__(WF_THREADS, 2)
+k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
+  __shared__ __align__(128) uint32_t buf[2][FB_BOX_WORDS];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ int s_bbox[6];
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x;
+  const int lx = tid >> 6, ly = (tid >> 3) & 7, lz = tid & 7;
+  const int s = (lx + FB_HALO) * (FB_BOX * FB_BOX) + (ly + FB_HALO) * FB_BOX + (lz + FB_HALO);
+  // parameters.h:55-68 again, as compile-time immediates for the unrolled relaxation loop
+  constexpr int kd[24][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
+                             {-1, -1, 0}, {1, 1, 0}, {0, -1, -1}, {0, 1, 1}, {-1, 0, -1}, {1, 0, 1},
+                             {-1, 1, 0}, {1, -1, 0}, {0, -1, 1}, {0, 1, -1}, {1, 0, -1}, {-1, 0, 1},
+                             {-2, 0, 0}, {2, 0, 0}, {0, -2, 0}, {0, 2, 0}, {0, 0, -2}, {0, 0, 2}};
+
+  if (tid == 0) mbar_init(&mbar, 1);
+  __syncthreads();
+  unsigned parity = 0;
+  unsigned cur = 0, gen = 0;
+  unsigned long long my_changed = 0, my_visits = 0;
+  const unsigned stamp0 = a.ctr->gen_stamp;   // stamp of generation 0 (seeded by k_seed_inserts / k_delete_scan)
+
+  for (;;) {
+    const unsigned nwork = ld_cg_u32(&a.ctr->n_list[cur]);
+    if (nwork == 0) break;
+    const unsigned par = gen & 1u;
+    if (blockIdx.x == 0 && tid == 0) a.ctr->n_changed[par ^ 1u] = 0;   // last read two barriers ago
+
+    // ---------------- phase 1: relax every active tile against the previous generation
+    for (unsigned w = blockIdx.x; w < nwork; w += gridDim.x) {
+      const unsigned tile = ld_cg_u32(&a.list[cur][w]);
+      const int tzc = tile % g.tz, tyc = (tile / g.tz) % g.ty, txc = tile / (g.tz * g.ty);
+      const int x0 = txc * FB_TILE, y0 = tyc * FB_TILE, z0 = tzc * FB_TILE;
+      if (tid == 0) {
+        s_bbox[0] = s_bbox[2] = s_bbox[4] = 8; s_bbox[1] = s_bbox[3] = s_bbox[5] = -1;
+        mbar_expect_tx(&mbar, FB_BOX_WORDS * 4);
+        tma_load_box(buf[0], &tmap, z0 - FB_HALO, y0 - FB_HALO, x0 - FB_HALO, &mbar);
+      }
+      mbar_wait(&mbar, parity);
+      parity ^= 1u;
+      const int vx = x0 + lx, vy = y0 + ly, vz = z0 + lz;
+      const uint32_t orig = buf[0][s];
+      for (int k = tid; k < FB_BOX_WORDS; k += WF_THREADS) buf[1][k] = buf[0][k];   // halo must exist in both buffers
+      // A voxel relaxes iff it has been observed (unknown voxels are barriers: distance_ = -10000 is never > tmp,
+      // ESDFMap.cpp:382) and lies inside the update box (only in-box voxels are ever queued, ESDFMap.cpp:351,378).
+      const uint32_t ocode = orig & FB_CODE_MASK;
+      const bool updatable = ocode != FB_UNKNOWN && fb_in_range(g, vx, vy, vz);
+      unsigned nmask = 0xffffffu;
+      if (!g.box_is_full) {                                  // VoxInRange(new_pos), ESDFMap.cpp:351
+        nmask = 0;
+#pragma unroll
+        for (int k = 0; k < 24; ++k)
+          if (fb_in_range(g, vx + kd[k][0], vy + kd[k][1], vz + kd[k][2])) nmask |= 1u << k;
+      }
+      __syncthreads();
+      uint32_t mine = ocode;                                 // code without the flag
+      uint32_t fresh = orig >> 31;                           // changed in the previous generation (global flag)
+      int cb = 0;
+      for (;;) {
+        uint32_t best = mine;
+        if (updatable) {
+          unsigned bestd = 0xffffffffu;
+          if (mine >= 2u) { int ox, oy, oz; fb_unpack(mine, ox, oy, oz); ox -= vx; oy -= vy; oz -= vz; bestd = (unsigned)(ox * ox + oy * oy + oz * oz); }
+          const uint32_t *b = buf[cb];
+#pragma unroll
+          for (int k = 0; k < 24; ++k) {
+            const uint32_t wn = b[s + kd[k][0] * (FB_BOX * FB_BOX) + kd[k][1] * FB_BOX + kd[k][2]];
+            const uint32_t c = wn & FB_CODE_MASK;
+            // candidate iff the neighbour has a closest obstacle (ESDFMap.cpp:353) and either it is in the queue (its
+            // push phase, :375-391) or this voxel is (its pull phase, :349-367)
+            if (c >= 2u && ((nmask >> k) & 1u) && ((wn >> 31) | fresh)) {
+              int ox, oy, oz; fb_unpack(c, ox, oy, oz); ox -= vx; oy -= vy; oz -= vz;
+              const unsigned d = (unsigned)(ox * ox + oy * oy + oz * oz);
+              if (d < bestd || (d == bestd && c < best)) { bestd = d; best = c; }   // strict improvement; ties -> smallest coordinate
+            }
+          }
+        }
+        fresh = best != mine ? 1u : 0u;
+        buf[cb ^ 1][s] = best | (fresh << 31);
+        const int any = __syncthreads_or((int)fresh);
+        mine = best;
+        cb ^= 1;
+        if (!any) break;
+      }
+      const bool changed = mine != ocode;                    // changed during this generation -> FRESH for the next one
+      const uint32_t outw = mine | (changed ? FB_FRESH : 0u);
+      if (changed) {
+        atomicMin(&s_bbox[0], lx); atomicMax(&s_bbox[1], lx);
+        atomicMin(&s_bbox[2], ly); atomicMax(&s_bbox[3], ly);
+        atomicMin(&s_bbox[4], lz); atomicMax(&s_bbox[5], lz);
+      }
+      const int nchanged = __syncthreads_count(changed);
+      const int dirty = __syncthreads_or(outw != orig);      // also true when only stale FRESH flags must be cleared
+      if (dirty && fb_in_grid(g, vx, vy, vz)) a.cobs_b[fb_ii(g, vx, vy, vz)] = outw;   // stage the whole tile interior
+      if (tid == 0) {
+        ++my_visits;
+        if (dirty) {
+          my_changed += (unsigned long long)nchanged;
+          const unsigned slot = atomicAdd(&a.ctr->n_changed[par], 1u);
+          a.changed[par][slot] = tile;
+          a.changed_bbox[par][slot] = nchanged ? ((unsigned)s_bbox[0] | ((unsigned)s_bbox[1] << 3) | ((unsigned)s_bbox[2] << 6) |
+                                                  ((unsigned)s_bbox[3] << 9) | ((unsigned)s_bbox[4] << 12) | ((unsigned)s_bbox[5] << 15) | (1u << 18))
+                                               : 0u;
+        }
+      }
+      // generic-proxy writes to buf[] must be ordered before the next async-proxy (TMA) write into buf[0]
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+    }
+    grid.sync();
+
+    // ---------------- phase 2: commit changed tiles, activate their neighbours for the next generation
+    if (blockIdx.x == 0 && tid == 0) a.ctr->n_list[cur] = 0;    // consumed; becomes the append target two phases from now
+    const unsigned nchg = ld_cg_u32(&a.ctr->n_changed[par]);
+    const unsigned stamp = stamp0 + gen + 1u;
+    for (unsigned w = blockIdx.x; w < nchg; w += gridDim.x) {
+      const unsigned tile = ld_cg_u32(&a.changed[par][w]);
+      const unsigned bb = ld_cg_u32(&a.changed_bbox[par][w]);
+      const int tzc = tile % g.tz, tyc = (tile / g.tz) % g.ty, txc = tile / (g.tz * g.ty);
+      const int vx = txc * FB_TILE + lx, vy = tyc * FB_TILE + ly, vz = tzc * FB_TILE + lz;
+      if (fb_in_grid(g, vx, vy, vz)) {
+        const long long ii = fb_ii(g, vx, vy, vz);
+        a.cobs[ii] = __ldcg(&a.cobs_b[ii]);
+      }
+      if (tid < 27 && (bb >> 18)) {                            // some record changed: its new value must reach the neighbours
+        const int ox = tid / 9 - 1, oy = (tid / 3) % 3 - 1, oz = tid % 3 - 1;
+        const int nz = (ox != 0) + (oy != 0) + (oz != 0);
+        if (nz == 0) fb_activate(a, tile, stamp, (int)(cur ^ 1u));   // revisit once more to clear the FRESH flags
+        if (nz == 1 || nz == 2) {                              // no 3-D corner directions in dirs_
+          const int mnx = bb & 7, mxx = (bb >> 3) & 7, mny = (bb >> 6) & 7, mxy = (bb >> 9) & 7, mnz = (bb >> 12) & 7, mxz = (bb >> 15) & 7;
+          bool need = true;
+          if (ox < 0) need = need && (mnx < 2); if (ox > 0) need = need && (mxx > 5);
+          if (oy < 0) need = need && (mny < 2); if (oy > 0) need = need && (mxy > 5);
+          if (oz < 0) need = need && (mnz < 2); if (oz > 0) need = need && (mxz > 5);
+          const int nx = txc + ox, ny = tyc + oy, nzc = tzc + oz;
+          if (need && nx >= 0 && nx < g.tx && ny >= 0 && ny < g.ty && nzc >= 0 && nzc < g.tz)
+            fb_activate(a, (unsigned)((nx * g.ty + ny) * g.tz + nzc), stamp, (int)(cur ^ 1u));
+        }
+      }
+    }
+    grid.sync();
+    cur ^= 1u;
+    ++gen;
+  }
+  if (tid == 0) {
+    if (my_changed) atomicAdd(&a.ctr->voxels_changed, my_changed);
+    if (my_visits) atomicAdd(&a.ctr->tile_visits, my_visits);
+    if (blockIdx.x == 0) { a.ctr->generations = gen; a.ctr->gen_stamp = stamp0 + gen + 1u; }
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+cudaError_t fb_esdf_make_tensor_map(CUtensorMap *out, const FbGeom &g, uint32_t *cobs, char *err, int errlen) {
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr) { snprintf(err, errlen, "cuTensorMapEncodeTiled entry point unavailable"); return e != cudaSuccess ? e : cudaErrorUnknown; }
+  cuuint64_t dims[3] = {(cuuint64_t)g.gz, (cuuint64_t)g.gy, (cuuint64_t)g.gx};
+  cuuint64_t strides[2] = {(cuuint64_t)g.pz * 4ull, (cuuint64_t)g.pz * (cuuint64_t)g.gy * 4ull};
+  cuuint32_t box[3] = {FB_BOX, FB_BOX, FB_BOX};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = ((PFN_encodeTiled)fn)(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, cobs, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return cudaErrorInvalidValue; }
+  return cudaSuccess;
+}
+
+cudaError_t fb_esdf_seed_inserts(const FbGeom &g, const FbEsdfArgs &a, const uint32_t *ins, unsigned n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  k_seed_inserts<<<(n + 255) / 256, 256, 0, s>>>(g, a, ins, n);
+  return cudaGetLastError();
+}
+
+cudaError_t fb_esdf_delete_scan(const FbGeom &g, const FbEsdfArgs &a, cudaStream_t s) {
+  long long nvec = g.ptotal >> 2;
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;                   // grid-stride, a multiple of the SM count
+  k_delete_scan<<<(unsigned)blocks, 256, 0, s>>>(g, a);
+  return cudaGetLastError();
+}
+
+int fb_esdf_wavefront_blocks(int device) {
+  int per_sm = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wavefront, WF_THREADS, 0) != cudaSuccess) return 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  return per_sm * sms;                                        // every block co-resident: required by grid.sync()
+}
+
+cudaError_t fb_esdf_wavefront(const FbGeom &g, const FbEsdfArgs &a, const CUtensorMap &tmap, int nblocks, cudaStream_t s) {
+  void *args[] = {(void *)&tmap, (void *)&g, (void *)&a};
+  return cudaLaunchCooperativeKernel((void *)k_wavefront, dim3(nblocks), dim3(WF_THREADS), args, 0, s);
+}

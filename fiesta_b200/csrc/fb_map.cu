@@ -1,0 +1,696 @@
+// fiesta_b200 -- C ABI (include/fiesta_b200.h), host-side map state, and the occupancy / query / export kernels.
+//
+// Host code mirrors what the reference does on the caller's thread with pure arithmetic (index conversions,
+// update-range bookkeeping, sentinel returns: /root/reference/src/ESDFMap.cpp:46-118, 401-421, 792-824) and hands every
+// per-voxel operation to the device.  There is NO CPU fallback: fiesta_create fails without an sm_100 device.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <new>
+#include "../../include/fiesta_b200.h"
+#include "fb_common.cuh"
+
+static thread_local std::string g_last_error;
+static void set_error(const char *fmt, const char *a = "", const char *b = "") {
+  char buf[512];
+  snprintf(buf, sizeof(buf), fmt, a, b);
+  g_last_error = buf;
+}
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) { set_error("%s failed: %s", #call, cudaGetErrorString(e__)); return FIESTA_ERR_CUDA; } \
+  } while (0)
+
+struct fiesta_map {
+  FbGeom g;
+  int device;
+  cudaStream_t stream;
+  bool params_set;
+  double l_hit, l_miss, l_min, l_max, l_occ;
+  double l_cornor[3], r_cornor[3];
+  // per-voxel state
+  uint32_t *cobs, *cobs_b, *stamp[2], *occbits;
+  double *occ;
+  unsigned long long *cnt;
+  // tiles
+  uint32_t *tile_flag, *list[2], *changed[2], *changed_bbox[2];
+  CUtensorMap tmap;
+  int wf_blocks, rr_blocks;
+  // queues
+  uint32_t *touched;
+  uint32_t *ins, *del;
+  size_t cap_ins, cap_del;
+  unsigned n_touched, n_ins, n_del;      // host view (valid after the last sync)
+  FbCounters *d_ctr, *h_ctr;
+  // per-call SetOccupancy staging
+  uint32_t *h_ev, *d_ev;
+  size_t n_ev, cap_ev;
+  // ray casting
+  float *d_xyz; size_t cap_xyz;
+  uint32_t *ray_list; size_t cap_ray_list;
+  int *ray_len, *ray_reach; size_t cap_rays;
+  unsigned tag_base;
+  // queries
+  double *d_qin, *d_qout; size_t cap_q;
+  cudaEvent_t ev[4];
+  fiesta_stats st;
+};
+
+// ====================================================================== kernels
+__global__ void k_reset_ray_ctr(FbCounters *c) {
+  c->ray_flag[0] = c->ray_flag[1] = c->ray_flag[2] = 0;
+  c->rays_cast = c->rays_dropped = c->ray_rounds = c->ray_error = 0;
+  c->ray_voxels = 0;
+}
+__global__ void k_reset_esdf_ctr(FbCounters *c) {
+  c->n_changed[0] = c->n_changed[1] = 0;
+  c->generations = 0;
+  c->voxels_changed = c->voxels_reset = c->tile_visits = 0;
+}
+__global__ void k_reset_queues(FbCounters *c, int touched, int insdel) {
+  if (touched) c->n_touched = 0;
+  if (insdel) c->n_ins = c->n_del = 0;
+}
+
+// O1 counter part for per-call SetOccupancy events staged on the host (ESDFMap.cpp:424-435).
+__global__ void k_apply_events(const uint32_t *ev, size_t n, unsigned long long *cnt, uint32_t *touched, FbCounters *ctr) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool first = false;
+  uint32_t ii = 0;
+  if (i < n) {
+    const uint32_t e = ev[i];
+    ii = e & 0x7fffffffu;
+    const unsigned long long old = atomicAdd(&cnt[ii], ((unsigned long long)(e >> 31) << 32) | 1ull);
+    first = (unsigned)(old & 0xffffffffull) == 0u;
+  }
+  const unsigned slot = fb_warp_append(&ctr->n_touched, first);
+  if (first) touched[slot] = ii;
+}
+
+// O2: ESDFMap::UpdateOccupancy (ESDFMap.cpp:235-271), one thread per queued voxel.  Voxels are independent, so the
+// queue order does not matter for the result.
+__global__ void k_integrate(FbGeom g, const uint32_t *touched, unsigned n, unsigned long long *cnt, double *occ, uint32_t *cobs,
+                            uint32_t *occbits, uint32_t *ins, uint32_t *del, FbCounters *ctr, int global_map, double l_hit,
+                            double l_miss, double l_min, double l_max, double l_occ) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool push_ins = false, push_del = false;
+  uint32_t ii = 0;
+  if (i < n) {
+    ii = touched[i];
+    const unsigned long long c = cnt[ii];
+    const long long hit = (long long)(c >> 32), tot = (long long)(c & 0xffffffffull);
+    cnt[ii] = 0ull;                                                       // num_hit_ = num_miss_ = 0
+    const double upd = (hit >= tot - hit) ? l_hit : l_miss;               // majority vote, ties -> hit (:243)
+    if (cobs[ii] == FB_UNKNOWN) cobs[ii] = FB_INF;                        // first observation: distance_ = +infinity_ (:246-249)
+    double o = occ[ii];
+    const bool was = o > l_occ;                                           // Exist(idx) before (:242)
+    bool skip = (upd >= 0 && o >= l_max) || (upd <= 0 && o <= l_min);     // already clamped in that direction (:250-255)
+    if (!skip) {
+      if (!global_map) {                                                  // local map: forget voxels outside the previous box (:256-259)
+        const int z = ii % g.pz, y = (ii / g.pz) % g.gy, x = ii / (g.pz * g.gy);
+        if (!fb_in_last_range(g, x, y, z)) { o = 0; cobs[ii] = FB_INF; }
+      }
+      double s = o + upd;
+      s = s > l_min ? s : l_min;
+      s = s < l_max ? s : l_max;
+      occ[ii] = s;
+      const bool now = s > l_occ;
+      if (now && !was) { push_ins = true; atomicOr(&occbits[ii >> 5], 1u << (ii & 31)); }        // insert_queue_.push (:263-264)
+      else if (!now && was) { push_del = true; atomicAnd(&occbits[ii >> 5], ~(1u << (ii & 31))); } // delete_queue_.push (:265-266)
+    }
+  }
+  const unsigned si = fb_warp_append(&ctr->n_ins, push_ins);
+  if (push_ins) ins[si] = ii;
+  const unsigned sd = fb_warp_append(&ctr->n_del, push_del);
+  if (push_del) del[sd] = ii;
+}
+
+// distance_buffer_ value of a record (ESDFMap.cpp:122-123, 198, 247): exact because the stored obstacle coordinate is exact.
+__device__ __forceinline__ double fb_record_distance(uint32_t c, int x, int y, int z, double res) {
+  c &= FB_CODE_MASK;
+  if (c == FB_UNKNOWN) return (double)FIESTA_UNDEFINED;
+  if (c == FB_INF) return (double)FIESTA_INFINITY;
+  int ox, oy, oz;
+  fb_unpack(c, ox, oy, oz);
+  const double dx = (double)(ox - x), dy = (double)(oy - y), dz = (double)(oz - z);
+  return sqrt((dx * dx + dy * dy) + dz * dz) * res;
+}
+
+__global__ void k_export(FbGeom g, const uint32_t *cobs, const double *occ, const unsigned long long *cnt, double *out_dist,
+                         int *out_cobs, double *out_occ, int *out_hit, int *out_tot) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // reference linear index
+  if (idx >= g.total) return;
+  const int x = (int)(idx / g.gyz), y = (int)(idx % g.gyz / g.gz), z = (int)(idx % g.gz);
+  const long long ii = fb_ii(g, x, y, z);
+  if (out_dist) out_dist[idx] = fb_record_distance(cobs[ii], x, y, z, g.res);
+  if (out_cobs) {
+    const uint32_t c = cobs[ii] & FB_CODE_MASK;
+    int ox = FIESTA_UNDEFINED, oy = FIESTA_UNDEFINED, oz = FIESTA_UNDEFINED;
+    if (c >= 2u) fb_unpack(c, ox, oy, oz);
+    out_cobs[3 * idx] = ox; out_cobs[3 * idx + 1] = oy; out_cobs[3 * idx + 2] = oz;
+  }
+  if (out_occ) out_occ[idx] = occ[ii];
+  if (out_hit) { const unsigned long long c = cnt[ii]; out_hit[idx] = (int)(c >> 32); out_tot[idx] = (int)(c & 0xffffffffull); }
+}
+
+// GetDistance(Vector3i) (ESDFMap.cpp:477-479): unknown reads +infinity_.  Out-of-grid coordinates (undefined behaviour
+// in the reference) also read +infinity_.
+__device__ __forceinline__ double fb_get_distance_vox(const FbGeom &g, const uint32_t *cobs, int x, int y, int z) {
+  if (!fb_in_grid(g, x, y, z)) return (double)FIESTA_INFINITY;
+  const double d = fb_record_distance(__ldg(&cobs[fb_ii(g, x, y, z)]), x, y, z, g.res);
+  return d < 0 ? (double)FIESTA_INFINITY : d;
+}
+__device__ __forceinline__ bool fb_pos_in_map(const FbGeom &g, const double *p) {
+  if (p[0] < g.min_range[0] || p[1] < g.min_range[1] || p[2] < g.min_range[2]) return false;
+  if (p[0] > g.max_range[0] || p[1] > g.max_range[1] || p[2] > g.max_range[2]) return false;
+  return true;
+}
+
+// mode 0: GetDistance(Vector3d)  (ESDFMap.cpp:467-475)      out[i]
+// mode 1: GetDistWithGradTrilinear (ESDFMap.cpp:481-540)    out[i], grad[3i..]
+// mode 2: GetOccupancy(Vector3d)  (ESDFMap.cpp:452-460)      out[i] = 0/1/-10000
+__global__ void k_query(FbGeom g, const uint32_t *cobs, const double *occ, double l_occ, const double *pos, long long n, int mode,
+                        double *out, double *grad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double p[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+  if (mode == 0 || mode == 2) {
+    if (!fb_pos_in_map(g, p)) { out[i] = (double)FIESTA_UNDEFINED; return; }
+    const int x = (int)floor((p[0] - g.origin[0]) / g.res), y = (int)floor((p[1] - g.origin[1]) / g.res), z = (int)floor((p[2] - g.origin[2]) / g.res);
+    if (mode == 0) out[i] = fb_get_distance_vox(g, cobs, x, y, z);
+    else out[i] = fb_in_grid(g, x, y, z) ? (occ[fb_ii(g, x, y, z)] > l_occ ? 1.0 : 0.0) : 0.0;
+    return;
+  }
+  if (!fb_pos_in_map(g, p)) { out[i] = -1.0; grad[3 * i] = grad[3 * i + 1] = grad[3 * i + 2] = 0.0; return; }
+  int b[3];
+  double bp[3], f[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double pm = p[k] - 0.5 * g.res * 1.0;                           // pos - 0.5*resolution_*Ones()
+    b[k] = (int)floor((pm - g.origin[k]) / g.res);
+    bp[k] = (b[k] + 0.5) * g.res + g.origin[k];                           // Vox2Pos
+    f[k] = (p[k] - bp[k]) * g.res_inv;
+  }
+  double c[2][2][2];
+#pragma unroll
+  for (int x = 0; x < 2; ++x)
+#pragma unroll
+    for (int y = 0; y < 2; ++y)
+#pragma unroll
+      for (int z = 0; z < 2; ++z) c[x][y][z] = fb_get_distance_vox(g, cobs, b[0] + x, b[1] + y, b[2] + z);
+  const double v00 = (1 - f[0]) * c[0][0][0] + f[0] * c[1][0][0];
+  const double v01 = (1 - f[0]) * c[0][0][1] + f[0] * c[1][0][1];
+  const double v10 = (1 - f[0]) * c[0][1][0] + f[0] * c[1][1][0];
+  const double v11 = (1 - f[0]) * c[0][1][1] + f[0] * c[1][1][1];
+  const double v0 = (1 - f[1]) * v00 + f[1] * v10;
+  const double v1 = (1 - f[1]) * v01 + f[1] * v11;
+  out[i] = (1 - f[2]) * v0 + f[2] * v1;
+  grad[3 * i + 2] = (v1 - v0) * g.res_inv;
+  grad[3 * i + 1] = ((1 - f[2]) * (v10 - v00) + f[2] * (v11 - v01)) * g.res_inv;
+  double g0 = (1 - f[2]) * (1 - f[1]) * (c[1][0][0] - c[0][0][0]);
+  g0 += (1 - f[2]) * f[1] * (c[1][1][0] - c[0][1][0]);
+  g0 += f[2] * (1 - f[1]) * (c[1][0][1] - c[0][0][1]);
+  g0 += f[2] * f[1] * (c[1][1][1] - c[0][1][1]);
+  g0 *= g.res_inv;
+  grad[3 * i] = g0;
+}
+
+// ====================================================================== host helpers
+static void set_box_flag(FbGeom &g) {
+  g.box_is_full = g.min_vec[0] == 0 && g.min_vec[1] == 0 && g.min_vec[2] == 0 && g.max_vec[0] == g.gx - 1 &&
+                  g.max_vec[1] == g.gy - 1 && g.max_vec[2] == g.gz - 1;
+}
+static bool host_pos_in_map(const FbGeom &g, const double *p) {
+  for (int i = 0; i < 3; ++i) if (p[i] < g.min_range[i]) return false;
+  for (int i = 0; i < 3; ++i) if (p[i] > g.max_range[i]) return false;
+  return true;
+}
+static void host_pos2vox(const FbGeom &g, const double *p, int *v) {
+  for (int i = 0; i < 3; ++i) v[i] = (int)floor((p[i] - g.origin[i]) / g.res);
+}
+template <typename T>
+static int ensure(T **ptr, size_t *cap, size_t need, bool keep, cudaStream_t s) {
+  if (need <= *cap) return FIESTA_OK;
+  size_t ncap = need + need / 2 + 1024;
+  T *np = nullptr;
+  CK(cudaMalloc((void **)&np, ncap * sizeof(T)));
+  if (keep && *ptr && *cap) { CK(cudaMemcpyAsync(np, *ptr, *cap * sizeof(T), cudaMemcpyDeviceToDevice, s)); CK(cudaStreamSynchronize(s)); }
+  if (*ptr) cudaFree(*ptr);
+  *ptr = np; *cap = ncap;
+  return FIESTA_OK;
+}
+static int fetch_counters(fiesta_map *m) {
+  CK(cudaMemcpyAsync(m->h_ctr, m->d_ctr, sizeof(FbCounters), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  m->n_touched = m->h_ctr->n_touched; m->n_ins = m->h_ctr->n_ins; m->n_del = m->h_ctr->n_del;
+  return FIESTA_OK;
+}
+static int flush_events(fiesta_map *m) {
+  if (m->n_ev == 0) return FIESTA_OK;
+  CK(cudaMemcpyAsync(m->d_ev, m->h_ev, m->n_ev * sizeof(uint32_t), cudaMemcpyHostToDevice, m->stream));
+  k_apply_events<<<(unsigned)((m->n_ev + 255) / 256), 256, 0, m->stream>>>(m->d_ev, m->n_ev, m->cnt, m->touched, m->d_ctr);
+  m->st.kernel_launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(m->stream));                                   // the pinned buffer is reused immediately
+  m->n_ev = 0;
+  return FIESTA_OK;
+}
+static inline int stage_event(fiesta_map *m, const int *v, int occ) {
+  if (m->n_ev == m->cap_ev) { int r = flush_events(m); if (r) return r; }
+  const long long ii = fb_ii(m->g, v[0], v[1], v[2]);
+  m->h_ev[m->n_ev++] = (uint32_t)ii | ((uint32_t)occ << 31);
+  return FIESTA_OK;
+}
+// ESDFMap::SetOccupancy(Vector3i, int) (ESDFMap.cpp:417-437) -- host half: index + range test + staged event.
+static inline int host_set_occupancy_vox(fiesta_map *m, const int *v, int occ, int *ret) {
+  const FbGeom &g = m->g;
+  *ret = v[0] * g.gyz + v[1] * g.gz + v[2];                               // Vox2Idx (:91), returned even when not counted
+  if (!fb_in_range(g, v[0], v[1], v[2])) return FIESTA_OK;                // :420-421
+  if (!fb_in_grid(g, v[0], v[1], v[2])) return FIESTA_OK;                 // cannot happen for a box set through SetUpdateRange
+  return stage_event(m, v, occ & 1);
+}
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char *fiesta_last_error(void) { return g_last_error.c_str(); }
+
+void fiesta_destroy(fiesta_map *m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  void *dev[] = {m->cobs, m->cobs_b, m->stamp[0], m->stamp[1], m->occbits, m->occ, m->cnt, m->tile_flag, m->list[0], m->list[1],
+                 m->changed[0], m->changed[1], m->changed_bbox[0], m->changed_bbox[1], m->touched, m->ins, m->del, m->d_ctr, m->d_ev,
+                 m->d_xyz, m->ray_list, m->ray_len, m->ray_reach, m->d_qin, m->d_qout};
+  for (void *p : dev) if (p) cudaFree(p);
+  if (m->h_ctr) cudaFreeHost(m->h_ctr);
+  if (m->h_ev) cudaFreeHost(m->h_ev);
+  for (int i = 0; i < 4; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+int fiesta_create(const fiesta_config *cfg, fiesta_map **out) {
+  if (!cfg || !out) { set_error("fiesta_create: null argument"); return FIESTA_ERR_INVALID; }
+  *out = nullptr;
+  if (!(cfg->resolution > 0)) { set_error("fiesta_create: resolution must be > 0"); return FIESTA_ERR_INVALID; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+    set_error("fiesta_create: no CUDA device %s(this library has no CPU fallback)", ""); return FIESTA_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) { set_error("fiesta_create: device is not sm_100 (%s); this build only contains sm_100a code", prop.name); return FIESTA_ERR_NO_DEVICE; }
+  CK(cudaSetDevice(cfg->device));
+  fiesta_map *m = new (std::nothrow) fiesta_map();
+  if (!m) { set_error("out of host memory"); return FIESTA_ERR_INVALID; }
+  memset((void *)m, 0, sizeof(*m));
+  m->device = cfg->device;
+  FbGeom &g = m->g;
+  int gs[3];
+  for (int i = 0; i < 3; ++i) {                                           // ctor, ESDFMap.cpp:171-186
+    g.origin[i] = cfg->origin[i];
+    gs[i] = (int)ceil(cfg->map_size[i] / cfg->resolution);
+    g.min_range[i] = cfg->origin[i];
+    g.max_range[i] = cfg->origin[i] + cfg->map_size[i];
+    m->l_cornor[i] = cfg->origin[i];
+    m->r_cornor[i] = cfg->origin[i] + cfg->map_size[i];
+  }
+  g.res = cfg->resolution; g.res_inv = 1 / cfg->resolution;
+  if (gs[0] < 1 || gs[1] < 1 || gs[2] < 1 || gs[0] > FB_MAX_GX || gs[1] > FB_MAX_GY || gs[2] > FB_MAX_GZ) {
+    set_error("fiesta_create: grid exceeds the supported 2046 x 1024 x 1024 voxels"); delete m; return FIESTA_ERR_LIMIT;
+  }
+  g.gx = gs[0]; g.gy = gs[1]; g.gz = gs[2]; g.pz = (g.gz + 3) & ~3;
+  g.gyz = g.gy * g.gz;
+  const long long total = (long long)g.gx * g.gyz;
+  g.ptotal = (long long)g.gx * g.gy * g.pz;
+  if (total > 0x7fffffffLL || g.ptotal > (long long)FB_LIST_IDX_MASK) { set_error("fiesta_create: more than 2^30 voxels"); delete m; return FIESTA_ERR_LIMIT; }
+  g.total = (int)total;
+  g.tx = (g.gx + 7) / 8; g.ty = (g.gy + 7) / 8; g.tz = (g.gz + 7) / 8; g.ntiles = g.tx * g.ty * g.tz;
+  for (int i = 0; i < 3; ++i) { g.min_vec[i] = g.last_min_vec[i] = 0; }   // SetOriginalRange, ESDFMap.cpp:819-822
+  g.max_vec[0] = g.last_max_vec[0] = g.gx - 1; g.max_vec[1] = g.last_max_vec[1] = g.gy - 1; g.max_vec[2] = g.last_max_vec[2] = g.gz - 1;
+  set_box_flag(g);
+
+#define CKD(call)                                                                        \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) { set_error("%s failed: %s", #call, cudaGetErrorString(e__)); fiesta_destroy(m); return FIESTA_ERR_CUDA; } \
+  } while (0)
+  CKD(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; ++i) CKD(cudaEventCreate(&m->ev[i]));
+  const size_t P = (size_t)g.ptotal;
+  const size_t nbits = (P + 31) / 32;
+  CKD(cudaMalloc((void **)&m->cobs, P * 4)); CKD(cudaMalloc((void **)&m->cobs_b, P * 4));
+  CKD(cudaMalloc((void **)&m->stamp[0], P * 4)); CKD(cudaMalloc((void **)&m->stamp[1], P * 4));
+  CKD(cudaMalloc((void **)&m->occbits, nbits * 4));
+  CKD(cudaMalloc((void **)&m->occ, P * 8)); CKD(cudaMalloc((void **)&m->cnt, P * 8));
+  CKD(cudaMalloc((void **)&m->touched, P * 4));
+  CKD(cudaMalloc((void **)&m->tile_flag, (size_t)g.ntiles * 4));
+  for (int k = 0; k < 2; ++k) {
+    CKD(cudaMalloc((void **)&m->list[k], (size_t)g.ntiles * 4));
+    CKD(cudaMalloc((void **)&m->changed[k], (size_t)g.ntiles * 4));
+    CKD(cudaMalloc((void **)&m->changed_bbox[k], (size_t)g.ntiles * 4));
+  }
+  CKD(cudaMalloc((void **)&m->d_ctr, sizeof(FbCounters)));
+  CKD(cudaMallocHost((void **)&m->h_ctr, sizeof(FbCounters)));
+  m->cap_ev = 1u << 22;
+  CKD(cudaMallocHost((void **)&m->h_ev, m->cap_ev * 4)); CKD(cudaMalloc((void **)&m->d_ev, m->cap_ev * 4));
+  CKD(cudaMemsetAsync(m->cobs, 0, P * 4, m->stream)); CKD(cudaMemsetAsync(m->cobs_b, 0, P * 4, m->stream));
+  CKD(cudaMemsetAsync(m->stamp[0], 0, P * 4, m->stream)); CKD(cudaMemsetAsync(m->stamp[1], 0, P * 4, m->stream));
+  CKD(cudaMemsetAsync(m->occbits, 0, nbits * 4, m->stream));
+  CKD(cudaMemsetAsync(m->occ, 0, P * 8, m->stream)); CKD(cudaMemsetAsync(m->cnt, 0, P * 8, m->stream));
+  CKD(cudaMemsetAsync(m->tile_flag, 0, (size_t)g.ntiles * 4, m->stream));
+  memset(m->h_ctr, 0, sizeof(FbCounters));
+  m->h_ctr->gen_stamp = 1;
+  CKD(cudaMemcpyAsync(m->d_ctr, m->h_ctr, sizeof(FbCounters), cudaMemcpyHostToDevice, m->stream));
+  m->tag_base = 1;
+  char err[256];
+  if (fb_esdf_make_tensor_map(&m->tmap, g, m->cobs, err, sizeof(err)) != cudaSuccess) { set_error("%s", err); fiesta_destroy(m); return FIESTA_ERR_CUDA; }
+  m->wf_blocks = fb_esdf_wavefront_blocks(m->device);
+  m->rr_blocks = fb_ray_resolve_blocks(m->device);
+  if (m->wf_blocks <= 0 || m->rr_blocks <= 0) { set_error("cooperative kernels do not fit on this device"); fiesta_destroy(m); return FIESTA_ERR_CUDA; }
+  CKD(cudaStreamSynchronize(m->stream));
+#undef CKD
+  *out = m;
+  return FIESTA_OK;
+}
+
+int fiesta_set_parameters(fiesta_map *m, double p_hit, double p_miss, double p_min, double p_max, double p_occ) {
+  if (!m) return FIESTA_ERR_INVALID;
+  m->l_hit = log(p_hit / (1 - p_hit)); m->l_miss = log(p_miss / (1 - p_miss));     // Logit, ESDFMap.cpp:12-14
+  m->l_min = log(p_min / (1 - p_min)); m->l_max = log(p_max / (1 - p_max)); m->l_occ = log(p_occ / (1 - p_occ));
+  m->params_set = true;
+  return FIESTA_OK;
+}
+int fiesta_grid_total_size(const fiesta_map *m) { return m ? m->g.total : 0; }
+int fiesta_grid_size(const fiesta_map *m, int out[3]) {
+  if (!m || !out) return FIESTA_ERR_INVALID;
+  out[0] = m->g.gx; out[1] = m->g.gy; out[2] = m->g.gz;
+  return FIESTA_OK;
+}
+
+int fiesta_set_occupancy_vox(fiesta_map *m, const int vox[3], int occ) {
+  int ret = FIESTA_UNDEFINED;
+  if (host_set_occupancy_vox(m, vox, occ, &ret) != FIESTA_OK) return FIESTA_UNDEFINED;
+  return ret;
+}
+int fiesta_set_occupancy_pos(fiesta_map *m, const double pos[3], int occ) {
+  if (occ != 1 && occ != 0) return FIESTA_UNDEFINED;                      // "occ value error!", ESDFMap.cpp:402-405
+  if (!host_pos_in_map(m->g, pos)) return FIESTA_UNDEFINED;               // :407-410
+  int v[3];
+  host_pos2vox(m->g, pos, v);
+  return fiesta_set_occupancy_vox(m, v, occ);
+}
+int fiesta_set_occupancy_batch_vox(fiesta_map *m, const int *vox, const uint8_t *occ, int64_t n, int *out_idx) {
+  if (!m || (n > 0 && (!vox || !occ))) return FIESTA_ERR_INVALID;
+  for (int64_t i = 0; i < n; ++i) {
+    int ret;
+    int r = host_set_occupancy_vox(m, vox + 3 * i, occ[i], &ret);
+    if (r) return r;
+    if (out_idx) out_idx[i] = ret;
+  }
+  return FIESTA_OK;
+}
+int fiesta_set_occupancy_batch_pos(fiesta_map *m, const double *pos, const uint8_t *occ, int64_t n, int *out_idx) {
+  if (!m || (n > 0 && (!pos || !occ))) return FIESTA_ERR_INVALID;
+  for (int64_t i = 0; i < n; ++i) {
+    int ret = FIESTA_UNDEFINED;
+    if ((occ[i] == 0 || occ[i] == 1) && host_pos_in_map(m->g, pos + 3 * i)) {
+      int v[3];
+      host_pos2vox(m->g, pos + 3 * i, v);
+      int r = host_set_occupancy_vox(m, v, occ[i], &ret);
+      if (r) return r;
+    }
+    if (out_idx) out_idx[i] = ret;
+  }
+  return FIESTA_OK;
+}
+
+int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, const double T[16], const fiesta_raycast_params *p) {
+  if (!m || !T || !p || n < 0 || (n > 0 && !d_xyz)) { set_error("fiesta_raycast_frame: bad argument"); return FIESTA_ERR_INVALID; }
+  if (n >= (int64_t)FB_RAY_MASK) { set_error("fiesta_raycast_frame: more than 2^20-1 points per frame"); return FIESTA_ERR_LIMIT; }
+  CK(cudaSetDevice(m->device));
+  m->st.rays_cast = m->st.rays_dropped = m->st.ray_voxels = m->st.raycast_rounds = 0; m->st.ms_raycast = 0;
+  if (n == 0) return FIESTA_OK;
+  const FbGeom &g = m->g;
+  FbRayArgs a;
+  memset(&a, 0, sizeof(a));
+  a.xyz = d_xyz; a.n = n;
+  memcpy(a.T, T, sizeof(double) * 16);
+  for (int k = 0; k < 3; ++k) {
+    a.org[k] = T[4 * k + 3] / T[15];                                      // raycast_origin_, Fiesta.h:420
+    a.start[k] = a.org[k] / g.res;                                        // Fiesta.h:233-236
+    a.bmin[k] = m->l_cornor[k] / g.res;
+    a.bmax[k] = m->r_cornor[k] / g.res;
+  }
+  a.min_len = p->min_ray_length; a.max_len = p->max_ray_length;
+  double capd = ceil(1.7320508075688772 * (p->max_ray_length / g.res)) + 8.0;
+  if (!(capd < 1500.0)) capd = 1500.0;
+  if (capd < 1.0) capd = 1.0;
+  a.cap = (int)capd;
+  a.max_rounds = 1000;
+  if (m->tag_base + a.max_rounds + 2 > FB_MAX_TAG) {                      // stamp tags exhausted: clear and restart
+    CK(cudaMemsetAsync(m->stamp[0], 0, (size_t)g.ptotal * 4, m->stream));
+    CK(cudaMemsetAsync(m->stamp[1], 0, (size_t)g.ptotal * 4, m->stream));
+    m->tag_base = 1;
+  }
+  a.tag_base = m->tag_base;
+  int r;
+  size_t need_rays = (size_t)n;
+  if (need_rays > m->cap_rays) {
+    size_t c1 = m->cap_rays, c2 = m->cap_rays;
+    if ((r = ensure(&m->ray_len, &c1, need_rays, false, m->stream))) return r;
+    if ((r = ensure(&m->ray_reach, &c2, need_rays, false, m->stream))) return r;
+    m->cap_rays = c1 < c2 ? c1 : c2;
+  }
+  if ((r = ensure(&m->ray_list, &m->cap_ray_list, (size_t)a.cap * (size_t)n, false, m->stream))) return r;
+  a.cnt = m->cnt; a.stamp[0] = m->stamp[0]; a.stamp[1] = m->stamp[1];
+  a.touched = m->touched; a.touched_cap = (unsigned)(g.ptotal > 0xffffffffLL ? 0xffffffffu : (unsigned)g.ptotal);
+  a.ray_list = m->ray_list; a.ray_len = m->ray_len; a.ray_reach = m->ray_reach; a.ctr = m->d_ctr;
+  CK(cudaEventRecord(m->ev[0], m->stream));
+  k_reset_ray_ctr<<<1, 1, 0, m->stream>>>(m->d_ctr);
+  int launches = 1;
+  CK(fb_ray_frame(g, a, m->rr_blocks, m->stream, &launches));
+  m->st.kernel_launches += launches;
+  CK(cudaEventRecord(m->ev[1], m->stream));
+  if ((r = fetch_counters(m))) return r;
+  CK(cudaEventElapsedTime(&m->st.ms_raycast, m->ev[0], m->ev[1]));
+  m->tag_base += m->h_ctr->ray_rounds + 1;
+  m->st.rays_cast = m->h_ctr->rays_cast; m->st.rays_dropped = m->h_ctr->rays_dropped;
+  m->st.ray_voxels = (int64_t)m->h_ctr->ray_voxels; m->st.raycast_rounds = m->h_ctr->ray_rounds;
+  m->st.touched_voxels = m->n_touched;
+  if (m->h_ctr->ray_error == 3) { set_error("fiesta_raycast_frame: stamp resolution did not converge"); return FIESTA_ERR_LIMIT; }
+  return FIESTA_OK;
+}
+
+int fiesta_raycast_frame(fiesta_map *m, const float *xyz, int64_t n, const double T[16], const fiesta_raycast_params *p) {
+  if (!m || n < 0 || (n > 0 && !xyz)) { set_error("fiesta_raycast_frame: bad argument"); return FIESTA_ERR_INVALID; }
+  CK(cudaSetDevice(m->device));
+  int r;
+  if ((r = ensure(&m->d_xyz, &m->cap_xyz, (size_t)n * 3, false, m->stream))) return r;
+  if (n) CK(cudaMemcpyAsync(m->d_xyz, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  return fiesta_raycast_frame_device(m, m->d_xyz, n, T, p);
+}
+
+int fiesta_check_update(fiesta_map *m) {
+  if (!m) return 0;
+  return (m->n_ev > 0 || m->n_touched > 0) ? 1 : 0;                       // !occupancy_queue_.empty(), ESDFMap.cpp:229
+}
+
+int fiesta_update_occupancy(fiesta_map *m, int global_map) {
+  if (!m) return -FIESTA_ERR_INVALID;
+  if (!m->params_set) { set_error("fiesta_update_occupancy: SetParameters was never called"); return -FIESTA_ERR_INVALID; }
+  if (cudaSetDevice(m->device) != cudaSuccess) return -FIESTA_ERR_CUDA;
+  int r;
+  cudaEventRecord(m->ev[0], m->stream);
+  if ((r = flush_events(m))) return -r;
+  if ((r = fetch_counters(m))) return -r;
+  const unsigned n = m->n_touched;
+  m->st.occupancy_updates = n;
+  if (n) {
+    if ((r = ensure(&m->ins, &m->cap_ins, (size_t)m->n_ins + n, true, m->stream))) return -r;
+    if ((r = ensure(&m->del, &m->cap_del, (size_t)m->n_del + n, true, m->stream))) return -r;
+    k_integrate<<<(n + 255) / 256, 256, 0, m->stream>>>(m->g, m->touched, n, m->cnt, m->occ, m->cobs, m->occbits, m->ins, m->del, m->d_ctr,
+                                                       global_map, m->l_hit, m->l_miss, m->l_min, m->l_max, m->l_occ);
+    k_reset_queues<<<1, 1, 0, m->stream>>>(m->d_ctr, 1, 0);
+    m->st.kernel_launches += 2;
+    if (cudaGetLastError() != cudaSuccess) { set_error("k_integrate launch failed"); return -FIESTA_ERR_CUDA; }
+  }
+  cudaEventRecord(m->ev[1], m->stream);
+  if ((r = fetch_counters(m))) return -r;
+  cudaEventElapsedTime(&m->st.ms_update_occupancy, m->ev[0], m->ev[1]);
+  m->st.touched_voxels = m->n_touched;
+  return (m->n_ins > 0 || m->n_del > 0) ? 1 : 0;                          // :270
+}
+
+int fiesta_update_esdf(fiesta_map *m) {
+  if (!m) return FIESTA_ERR_INVALID;
+  CK(cudaSetDevice(m->device));
+  m->st.inserts = m->n_ins; m->st.deletes = m->n_del;
+  m->st.voxels_changed = m->st.voxels_reset = m->st.tile_visits = m->st.generations = 0;
+  m->st.ms_update_esdf = m->st.ms_esdf_delete_scan = m->st.ms_esdf_wavefront = 0;
+  if (m->n_ins == 0 && m->n_del == 0) return FIESTA_OK;
+  FbEsdfArgs a;
+  a.cobs = m->cobs; a.cobs_b = m->cobs_b; a.occ = m->occ; a.occbits = m->occbits; a.tile_flag = m->tile_flag;
+  for (int k = 0; k < 2; ++k) { a.list[k] = m->list[k]; a.changed[k] = m->changed[k]; a.changed_bbox[k] = m->changed_bbox[k]; }
+  a.ctr = m->d_ctr; a.l_occ = m->l_occ;
+  CK(cudaEventRecord(m->ev[0], m->stream));
+  k_reset_esdf_ctr<<<1, 1, 0, m->stream>>>(m->d_ctr);
+  m->st.kernel_launches++;
+  if (m->n_ins) { CK(fb_esdf_seed_inserts(m->g, a, m->ins, m->n_ins, m->stream)); m->st.kernel_launches++; }   // E1
+  CK(cudaEventRecord(m->ev[1], m->stream));
+  if (m->n_del) { CK(fb_esdf_delete_scan(m->g, a, m->stream)); m->st.kernel_launches++; }                      // E2
+  CK(cudaEventRecord(m->ev[2], m->stream));
+  CK(fb_esdf_wavefront(m->g, a, m->tmap, m->wf_blocks, m->stream));                                           // E3
+  m->st.kernel_launches++;
+  k_reset_queues<<<1, 1, 0, m->stream>>>(m->d_ctr, 0, 1);
+  m->st.kernel_launches++;
+  CK(cudaEventRecord(m->ev[3], m->stream));
+  int r;
+  if ((r = fetch_counters(m))) return r;
+  CK(cudaEventElapsedTime(&m->st.ms_update_esdf, m->ev[0], m->ev[3]));
+  CK(cudaEventElapsedTime(&m->st.ms_esdf_delete_scan, m->ev[1], m->ev[2]));
+  CK(cudaEventElapsedTime(&m->st.ms_esdf_wavefront, m->ev[2], m->ev[3]));
+  m->st.voxels_changed = (int64_t)m->h_ctr->voxels_changed; m->st.voxels_reset = (int64_t)m->h_ctr->voxels_reset;
+  m->st.tile_visits = (int64_t)m->h_ctr->tile_visits; m->st.generations = m->h_ctr->generations;
+  return FIESTA_OK;
+}
+
+int fiesta_set_update_range(fiesta_map *m, const double min_pos[3], const double max_pos[3], int new_vec) {
+  if (!m || !min_pos || !max_pos) return FIESTA_ERR_INVALID;
+  FbGeom &g = m->g;
+  double lo[3], hi[3];
+  for (int i = 0; i < 3; ++i) {                                           // ESDFMap.cpp:794-800
+    lo[i] = min_pos[i] > g.min_range[i] ? min_pos[i] : g.min_range[i];
+    hi[i] = max_pos[i] < g.max_range[i] ? max_pos[i] : g.max_range[i];
+  }
+  if (new_vec) for (int i = 0; i < 3; ++i) { g.last_min_vec[i] = g.min_vec[i]; g.last_max_vec[i] = g.max_vec[i]; }
+  host_pos2vox(g, lo, g.min_vec);
+  for (int i = 0; i < 3; ++i) hi[i] = hi[i] - g.res / 2;                   // :807-809
+  host_pos2vox(g, hi, g.max_vec);
+  set_box_flag(g);
+  return FIESTA_OK;
+}
+int fiesta_set_original_range(fiesta_map *m) {
+  if (!m) return FIESTA_ERR_INVALID;
+  FbGeom &g = m->g;
+  for (int i = 0; i < 3; ++i) g.min_vec[i] = g.last_min_vec[i] = 0;
+  g.max_vec[0] = g.last_max_vec[0] = g.gx - 1; g.max_vec[1] = g.last_max_vec[1] = g.gy - 1; g.max_vec[2] = g.last_max_vec[2] = g.gz - 1;
+  set_box_flag(g);
+  return FIESTA_OK;
+}
+
+// ---- queries
+static int run_query(fiesta_map *m, const double *pos, int64_t n, int mode, double *out, double *grad) {
+  if (n <= 0) return FIESTA_OK;
+  CK(cudaSetDevice(m->device));
+  int r;
+  size_t c1 = m->cap_q, c2 = m->cap_q;
+  if ((size_t)n * 3 > m->cap_q) {
+    if ((r = ensure(&m->d_qin, &c1, (size_t)n * 3, false, m->stream))) return r;
+    if ((r = ensure(&m->d_qout, &c2, (size_t)n * 4, false, m->stream))) return r;   // [dist n][grad 3n]
+    m->cap_q = (c1 < c2 ? c1 : c2) * 3 / 4;
+    if (m->cap_q < (size_t)n * 3) m->cap_q = (size_t)n * 3;
+  }
+  CK(cudaMemcpyAsync(m->d_qin, pos, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  k_query<<<(unsigned)((n + 127) / 128), 128, 0, m->stream>>>(m->g, m->cobs, m->occ, m->l_occ, m->d_qin, n, mode, m->d_qout, m->d_qout + n);
+  m->st.kernel_launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, m->d_qout, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  if (grad) CK(cudaMemcpyAsync(grad, m->d_qout + n, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return FIESTA_OK;
+}
+double fiesta_get_distance_pos(fiesta_map *m, const double pos[3]) {
+  double d = FIESTA_UNDEFINED;
+  if (!m || run_query(m, pos, 1, 0, &d, nullptr)) return FIESTA_UNDEFINED;
+  return d;
+}
+double fiesta_get_distance_vox(fiesta_map *m, const int vox[3]) {
+  if (!m) return FIESTA_INFINITY;
+  const FbGeom &g = m->g;
+  if (!fb_in_grid(g, vox[0], vox[1], vox[2])) return FIESTA_INFINITY;
+  double p[3];
+  for (int i = 0; i < 3; ++i) p[i] = (vox[i] + 0.5) * g.res + g.origin[i];          // voxel centre maps back to the same voxel
+  int v[3];
+  host_pos2vox(g, p, v);
+  if (v[0] == vox[0] && v[1] == vox[1] && v[2] == vox[2] && host_pos_in_map(g, p)) return fiesta_get_distance_pos(m, p);
+  uint32_t c = 0;                                                         // pathological origin/resolution: read the record directly
+  if (cudaMemcpy(&c, m->cobs + fb_ii(g, vox[0], vox[1], vox[2]), 4, cudaMemcpyDeviceToHost) != cudaSuccess) return FIESTA_INFINITY;
+  c &= FB_CODE_MASK;
+  if (c < 2u) return FIESTA_INFINITY;
+  int ox, oy, oz; fb_unpack(c, ox, oy, oz);
+  const double dx = ox - vox[0], dy = oy - vox[1], dz = oz - vox[2];
+  return sqrt((dx * dx + dy * dy) + dz * dz) * g.res;
+}
+int fiesta_get_occupancy_pos(fiesta_map *m, const double pos[3]) {
+  double d = FIESTA_UNDEFINED;
+  if (!m || run_query(m, pos, 1, 2, &d, nullptr)) return FIESTA_UNDEFINED;
+  return (int)d;
+}
+int fiesta_get_occupancy_vox(fiesta_map *m, const int vox[3]) {
+  if (!m || !fb_in_grid(m->g, vox[0], vox[1], vox[2])) return 0;
+  double o = 0;
+  if (cudaMemcpy(&o, m->occ + fb_ii(m->g, vox[0], vox[1], vox[2]), 8, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  return o > m->l_occ ? 1 : 0;
+}
+double fiesta_get_dist_grad_trilinear(fiesta_map *m, const double pos[3], double grad[3]) {
+  double d = -1;
+  if (!m || run_query(m, pos, 1, 1, &d, grad)) return -1;
+  return d;
+}
+int fiesta_get_distance_batch_pos(fiesta_map *m, const double *pos, int64_t n, double *out) {
+  if (!m || (n > 0 && (!pos || !out))) return FIESTA_ERR_INVALID;
+  return run_query(m, pos, n, 0, out, nullptr);
+}
+int fiesta_get_dist_grad_trilinear_batch(fiesta_map *m, const double *pos, int64_t n, double *out, double *grad) {
+  if (!m || (n > 0 && (!pos || !out || !grad))) return FIESTA_ERR_INVALID;
+  return run_query(m, pos, n, 1, out, grad);
+}
+
+// ---- exports
+static int run_export(fiesta_map *m, double *dist, int *cobs3, double *occ, int *hit, int *tot) {
+  CK(cudaSetDevice(m->device));
+  const size_t G = (size_t)m->g.total;
+  double *dd = nullptr, *dof = nullptr; int *dc = nullptr, *dh = nullptr, *dt = nullptr;
+  if (dist) CK(cudaMalloc((void **)&dd, G * 8));
+  if (occ) CK(cudaMalloc((void **)&dof, G * 8));
+  if (cobs3) CK(cudaMalloc((void **)&dc, G * 12));
+  if (hit) { CK(cudaMalloc((void **)&dh, G * 4)); CK(cudaMalloc((void **)&dt, G * 4)); }
+  k_export<<<(unsigned)((G + 255) / 256), 256, 0, m->stream>>>(m->g, m->cobs, m->occ, m->cnt, dd, dc, dof, dh, dt);
+  m->st.kernel_launches++;
+  CK(cudaGetLastError());
+  if (dist) CK(cudaMemcpyAsync(dist, dd, G * 8, cudaMemcpyDeviceToHost, m->stream));
+  if (occ) CK(cudaMemcpyAsync(occ, dof, G * 8, cudaMemcpyDeviceToHost, m->stream));
+  if (cobs3) CK(cudaMemcpyAsync(cobs3, dc, G * 12, cudaMemcpyDeviceToHost, m->stream));
+  if (hit) { CK(cudaMemcpyAsync(hit, dh, G * 4, cudaMemcpyDeviceToHost, m->stream)); CK(cudaMemcpyAsync(tot, dt, G * 4, cudaMemcpyDeviceToHost, m->stream)); }
+  CK(cudaStreamSynchronize(m->stream));
+  cudaFree(dd); cudaFree(dof); cudaFree(dc); cudaFree(dh); cudaFree(dt);
+  return FIESTA_OK;
+}
+int fiesta_export_distance(fiesta_map *m, double *out) { return (!m || !out) ? FIESTA_ERR_INVALID : run_export(m, out, nullptr, nullptr, nullptr, nullptr); }
+int fiesta_export_closest_obstacle(fiesta_map *m, int *out) { return (!m || !out) ? FIESTA_ERR_INVALID : run_export(m, nullptr, out, nullptr, nullptr, nullptr); }
+int fiesta_export_occupancy(fiesta_map *m, double *out) { return (!m || !out) ? FIESTA_ERR_INVALID : run_export(m, nullptr, nullptr, out, nullptr, nullptr); }
+int fiesta_export_counters(fiesta_map *m, int *hit, int *tot) {
+  if (!m || !hit || !tot) return FIESTA_ERR_INVALID;
+  int r = flush_events(m);
+  if (r) return r;
+  return run_export(m, nullptr, nullptr, nullptr, hit, tot);
+}
+
+int fiesta_get_stats(fiesta_map *m, fiesta_stats *out) {
+  if (!m || !out) return FIESTA_ERR_INVALID;
+  *out = m->st;
+  return FIESTA_OK;
+}
+int fiesta_synchronize(fiesta_map *m) {
+  if (!m) return FIESTA_ERR_INVALID;
+  CK(cudaSetDevice(m->device));
+  CK(cudaStreamSynchronize(m->stream));
+  return FIESTA_OK;
+}
+
+}  // extern "C"

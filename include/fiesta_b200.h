@@ -1,0 +1,141 @@
+/*
+ * fiesta_b200 -- C ABI of the B200-native FIESTA hot path.
+ *
+ * This is the drop-in boundary: every entry point below replaces one method of the reference's
+ * `fiesta::ESDFMap` (or the one `Fiesta` member that drives it) and keeps its argument meaning, return
+ * sentinels and error behaviour.  Citations are into the reference tree (HKUST-Aerial-Robotics/FIESTA).
+ * Plain pointers and sizes only; no C++/torch types.  All functions are synchronous with respect to the
+ * caller unless stated otherwise (work is enqueued on the map's CUDA stream and waited for where a
+ * value is returned).
+ *
+ * Voxel index convention (ESDFMap.cpp:84-93): idx = x*Gy*Gz + y*Gz + z, z fastest.
+ * Sentinels (ESDFMap.cpp:181-185): -10000 = undefined / out of map, +10000 = infinity.
+ */
+#ifndef FIESTA_B200_H_
+#define FIESTA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fiesta_map fiesta_map;
+
+#define FIESTA_UNDEFINED (-10000)
+#define FIESTA_INFINITY (10000)
+
+enum {
+  FIESTA_OK = 0,
+  FIESTA_ERR_INVALID = 1,   /* bad argument */
+  FIESTA_ERR_CUDA = 2,      /* CUDA runtime/driver error, see fiesta_last_error() */
+  FIESTA_ERR_NO_DEVICE = 3, /* no usable sm_100 device: there is NO CPU fallback */
+  FIESTA_ERR_LIMIT = 4      /* grid or frame exceeds a documented limit */
+};
+
+/* ESDFMap::ESDFMap(origin, resolution, map_size) arguments (ESDFMap.h:116, ESDFMap.cpp:171-213) plus placement. */
+typedef struct fiesta_config {
+  double origin[3];     /* l_cornor_ : lower corner of the map, metres */
+  double resolution;    /* voxel edge, metres */
+  double map_size[3];   /* r_cornor_ - l_cornor_, metres; grid = ceil(map_size / resolution) */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t reserved[7];  /* must be zero */
+} fiesta_config;
+
+/* Fiesta::RaycastProcess parameters (parameters.h:148-149, Fiesta.h:209-245). */
+typedef struct fiesta_raycast_params {
+  double min_ray_length; /* parameters_.min_ray_length_ */
+  double max_ray_length; /* parameters_.max_ray_length_ */
+} fiesta_raycast_params;
+
+/* What the reference prints inside its hot path (ESDFMap.cpp:237,277,394) plus device timings. */
+typedef struct fiesta_stats {
+  int64_t occupancy_updates;   /* occupancy_queue_ size drained by the last UpdateOccupancy          (:237) */
+  int64_t inserts, deletes;    /* insert_queue_/delete_queue_ sizes seen by the last UpdateESDF        (:277) */
+  int64_t voxels_changed;      /* voxels whose (distance, closest obstacle) record changed in the last UpdateESDF */
+  int64_t voxels_reset;        /* dependants of deleted obstacles cleared by the last UpdateESDF (E2) */
+  int64_t tile_visits;         /* 8^3 tile relaxations run by the last UpdateESDF */
+  int64_t generations;         /* wavefront generations of the last UpdateESDF */
+  int64_t rays_cast;           /* rays traversed by the last raycast frame (after endpoint dedupe, Fiesta.h:221-231) */
+  int64_t rays_dropped;        /* rays the reference Raycast() would never return from / would throw on */
+  int64_t ray_voxels;          /* DDA voxels emitted by the last raycast frame */
+  int64_t raycast_rounds;      /* stamp-resolution rounds of the last raycast frame */
+  int64_t touched_voxels;      /* voxels currently waiting in the occupancy queue */
+  int64_t kernel_launches;     /* kernels launched by this map since creation */
+  float ms_raycast;            /* device time of the last raycast frame */
+  float ms_update_occupancy;   /* device time of the last UpdateOccupancy */
+  float ms_update_esdf;        /* device time of the last UpdateESDF (whole call) */
+  float ms_esdf_delete_scan;   /* ... of which: dense dependant scan (E2) */
+  float ms_esdf_wavefront;     /* ... of which: tile wavefront kernel (E3) */
+  float reserved_f[3];
+} fiesta_stats;
+
+/* ---- lifetime: `new ESDFMap(...)` / `delete` (Fiesta.h:96,137) ---- */
+int fiesta_create(const fiesta_config *cfg, fiesta_map **out);
+void fiesta_destroy(fiesta_map *m);
+/* Thread-local description of the last failure on this thread ("" if none). */
+const char *fiesta_last_error(void);
+
+/* ESDFMap::SetParameters (ESDFMap.h:124, ESDFMap.cpp:218-224). */
+int fiesta_set_parameters(fiesta_map *m, double p_hit, double p_miss, double p_min, double p_max, double p_occ);
+/* public field ESDFMap::grid_total_size_ (ESDFMap.h:115) and grid_size_ (ESDFMap.cpp:175-176). */
+int fiesta_grid_total_size(const fiesta_map *m);
+int fiesta_grid_size(const fiesta_map *m, int out[3]);
+
+/* ---- occupancy input ---- */
+/* int ESDFMap::SetOccupancy(Eigen::Vector3d pos, int occ) (ESDFMap.cpp:401-415): -10000 for occ not in {0,1} or pos
+ * outside the map, else the linear voxel index (also when the voxel is outside the update box and is not counted). */
+int fiesta_set_occupancy_pos(fiesta_map *m, const double pos[3], int occ);
+/* int ESDFMap::SetOccupancy(Eigen::Vector3i vox, int occ) (ESDFMap.cpp:417-437). */
+int fiesta_set_occupancy_vox(fiesta_map *m, const int vox[3], int occ);
+/* The same call for n events in order; out_idx (nullable) receives each return value. Host pointers. */
+int fiesta_set_occupancy_batch_pos(fiesta_map *m, const double *pos_xyz, const uint8_t *occ, int64_t n, int *out_idx);
+int fiesta_set_occupancy_batch_vox(fiesta_map *m, const int *vox_xyz, const uint8_t *occ, int64_t n, int *out_idx);
+
+/* Fiesta::RaycastMultithread + RaycastProcess, serial semantics (Fiesta.h:194-303), fused with Raycast()
+ * (raycast.cpp:56-158) and the counter part of SetOccupancy.  xyz: n points (pcl::PointXYZ, 3 floats each) in the
+ * sensor frame; T: row-major 4x4 `transform_` (Fiesta.h:415-419); raycast_origin_ = T[:3,3]/T[3,3] (Fiesta.h:420).
+ * `fiesta_raycast_frame` takes a HOST pointer (copied through a pinned staging buffer); `_device` takes a DEVICE
+ * pointer valid on the map's device and is asynchronous. */
+int fiesta_raycast_frame(fiesta_map *m, const float *xyz, int64_t n, const double T[16], const fiesta_raycast_params *p);
+int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, const double T[16],
+                                const fiesta_raycast_params *p);
+
+/* ---- per-frame driver: Fiesta::UpdateEsdfEvent (Fiesta.h:507-514) ---- */
+/* bool ESDFMap::CheckUpdate() (ESDFMap.cpp:227-233): 1 if the occupancy queue is non-empty. */
+int fiesta_check_update(fiesta_map *m);
+/* bool ESDFMap::UpdateOccupancy(bool global_map) (ESDFMap.cpp:235-271): 1 if inserts or deletes are pending, 0 if not,
+ * negative error code on failure. */
+int fiesta_update_occupancy(fiesta_map *m, int global_map);
+/* void ESDFMap::UpdateESDF() (ESDFMap.cpp:273-398). */
+int fiesta_update_esdf(fiesta_map *m);
+/* ESDFMap::SetUpdateRange / SetOriginalRange (ESDFMap.cpp:792-824). */
+int fiesta_set_update_range(fiesta_map *m, const double min_pos[3], const double max_pos[3], int new_vec);
+int fiesta_set_original_range(fiesta_map *m);
+
+/* ---- queries (ESDFMap.cpp:452-540) ---- */
+double fiesta_get_distance_pos(fiesta_map *m, const double pos[3]);  /* -10000 outside the map; unknown reads +10000 */
+double fiesta_get_distance_vox(fiesta_map *m, const int vox[3]);
+int fiesta_get_occupancy_pos(fiesta_map *m, const double pos[3]);    /* -10000 outside the map, else 0/1 */
+int fiesta_get_occupancy_vox(fiesta_map *m, const int vox[3]);
+/* double ESDFMap::GetDistWithGradTrilinear(pos, grad) (ESDFMap.cpp:481-540): -1 outside the map. */
+double fiesta_get_dist_grad_trilinear(fiesta_map *m, const double pos[3], double grad[3]);
+/* Batched forms (host pointers): n positions -> n distances (+ n gradients). */
+int fiesta_get_distance_batch_pos(fiesta_map *m, const double *pos_xyz, int64_t n, double *out_dist);
+int fiesta_get_dist_grad_trilinear_batch(fiesta_map *m, const double *pos_xyz, int64_t n, double *out_dist,
+                                         double *out_grad_xyz);
+
+/* ---- state dumps in the reference's own representation (parity harness; host pointers, grid_total_size entries) ---- */
+int fiesta_export_distance(fiesta_map *m, double *out);             /* distance_buffer_: -10000 unknown, +10000 unreached */
+int fiesta_export_closest_obstacle(fiesta_map *m, int *out_xyz);    /* closest_obstacle_: 3 ints, -10000 = none */
+int fiesta_export_occupancy(fiesta_map *m, double *out);            /* occupancy_buffer_ log-odds */
+int fiesta_export_counters(fiesta_map *m, int *num_hit, int *num_total); /* num_hit_, num_miss_ (all observations) */
+
+int fiesta_get_stats(fiesta_map *m, fiesta_stats *out);
+/* Block until all work queued on the map's stream has finished. */
+int fiesta_synchronize(fiesta_map *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIESTA_B200_H_ */
