@@ -22,8 +22,10 @@
 #define FB_INF 1u
 #define FB_TILE 8
 #define FB_HALO 2
-#define FB_BOX (FB_TILE + 2 * FB_HALO)            // 12
-#define FB_BOX_WORDS (FB_BOX * FB_BOX * FB_BOX)   // 1728
+#define FB_BOX (FB_TILE + 2 * FB_HALO)            // 12 : x and y extent of the staged box
+#define FB_ZPAD 4                                 // TMA needs the innermost start coordinate 16-byte aligned: the box
+#define FB_BOXZ (FB_TILE + 2 * FB_ZPAD)           // 16   starts at z0 - 4 (not z0 - 2) and is 16 voxels long in z
+#define FB_BOX_WORDS (FB_BOX * FB_BOX * FB_BOXZ)  // 2304
 #define FB_FRESH 0x80000000u
 #define FB_CODE_MASK 0x7fffffffu
 #define FB_MAX_GX 2046

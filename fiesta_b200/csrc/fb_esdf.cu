@@ -7,7 +7,8 @@
 //                   relaxation below re-seeds them from valid neighbours.
 // E3 wavefront      (ESDFMap.cpp:338-392)  k_wavefront    : persistent cooperative kernel over a device work-list of
 //                   active 8^3 tiles.  Each tile (+2-voxel halo, because dirs_ contains the +-2 axis steps,
-//                   parameters.h:66-68) is staged into shared memory with ONE TMA box load (cp.async.bulk.tensor.3d;
+//                   parameters.h:66-68; 4 in z to keep TMA's 16-byte start alignment) is staged into shared memory with ONE TMA box
+//                   load (cp.async.bulk.tensor.3d;
 //                   out-of-grid voxels are zero-filled = "never observed" = barrier), relaxed to a local fixpoint with the
 //                   reference's 24-neighbourhood, strict-improvement rule and unknown-voxel barriers, written to a staging
 //                   grid if it changed, and after a grid-wide barrier committed and its neighbours activated for the next
@@ -104,7 +105,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
-// TMA: one 12x12x12 u32 box (z fastest) -> shared memory, completion signalled on `bar`.
+// TMA: one 12x12x16 (x,y,z; z fastest) u32 box -> shared memory, completion signalled on `bar`.
+// The innermost start coordinate must be a multiple of 4 elements (16 bytes) or the instruction faults.
 __device__ __forceinline__ void tma_load_box(void *dst, const CUtensorMap *tmap, int cz, int cy, int cx, uint64_t *bar) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
@@ -123,7 +125,7 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   const int lx = tid >> 6, ly = (tid >> 3) & 7, lz = tid & 7;
-  const int s = (lx + FB_HALO) * (FB_BOX * FB_BOX) + (ly + FB_HALO) * FB_BOX + (lz + FB_HALO);
+  const int s = (lx + FB_HALO) * (FB_BOX * FB_BOXZ) + (ly + FB_HALO) * FB_BOXZ + (lz + FB_ZPAD);
   // parameters.h:55-68 again, as compile-time immediates for the unrolled relaxation loop
   constexpr int kd[24][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
                              {-1, -1, 0}, {1, 1, 0}, {0, -1, -1}, {0, 1, 1}, {-1, 0, -1}, {1, 0, 1},
@@ -151,7 +153,7 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
       if (tid == 0) {
         s_bbox[0] = s_bbox[2] = s_bbox[4] = 8; s_bbox[1] = s_bbox[3] = s_bbox[5] = -1;
         mbar_expect_tx(&mbar, FB_BOX_WORDS * 4);
-        tma_load_box(buf[0], &tmap, z0 - FB_HALO, y0 - FB_HALO, x0 - FB_HALO, &mbar);
+        tma_load_box(buf[0], &tmap, z0 - FB_ZPAD, y0 - FB_HALO, x0 - FB_HALO, &mbar);
       }
       mbar_wait(&mbar, parity);
       parity ^= 1u;
@@ -181,7 +183,7 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
           const uint32_t *b = buf[cb];
 #pragma unroll
           for (int k = 0; k < 24; ++k) {
-            const uint32_t wn = b[s + kd[k][0] * (FB_BOX * FB_BOX) + kd[k][1] * FB_BOX + kd[k][2]];
+            const uint32_t wn = b[s + kd[k][0] * (FB_BOX * FB_BOXZ) + kd[k][1] * FB_BOXZ + kd[k][2]];
             const uint32_t c = wn & FB_CODE_MASK;
             // candidate iff the neighbour has a closest obstacle (ESDFMap.cpp:353) and either it is in the queue (its
             // push phase, :375-391) or this voxel is (its pull phase, :349-367)
@@ -278,7 +280,7 @@ cudaError_t fb_esdf_make_tensor_map(CUtensorMap *out, const FbGeom &g, uint32_t 
   if (e != cudaSuccess || fn == nullptr) { snprintf(err, errlen, "cuTensorMapEncodeTiled entry point unavailable"); return e != cudaSuccess ? e : cudaErrorUnknown; }
   cuuint64_t dims[3] = {(cuuint64_t)g.gz, (cuuint64_t)g.gy, (cuuint64_t)g.gx};
   cuuint64_t strides[2] = {(cuuint64_t)g.pz * 4ull, (cuuint64_t)g.pz * (cuuint64_t)g.gy * 4ull};
-  cuuint32_t box[3] = {FB_BOX, FB_BOX, FB_BOX};
+  cuuint32_t box[3] = {FB_BOXZ, FB_BOX, FB_BOX};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = ((PFN_encodeTiled)fn)(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, cobs, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

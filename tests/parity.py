@@ -28,7 +28,7 @@ def compare(dev, ora, check_counters=False):
     return res
 
 
-def assert_exact_distance(dev, ora, tag="", tie_frac_limit=0.10):
+def assert_exact_distance(dev, ora, tag="", tie_frac_limit=0.35):
     r = compare(dev, ora)
     assert r["occ"] == 0, (tag, r)
     assert r["dist"] == 0, (tag, r)
