@@ -31,9 +31,16 @@
 #define FB_MAX_GX 2046
 #define FB_MAX_GY 1024
 #define FB_MAX_GZ 1024
-#define FB_RAY_BITS 20                            // ray index bits inside a stamp
+// free-space claim word (stamp[0]): [frame tag:2 | ray index:19 | position in that ray's list:11]; 0 = never claimed.
+// endpoint owner word (stamp[1]):   [owner frame tag:13 | ~ray index:19], atomicMax keeps the newest frame / lowest ray.
+#define FB_RAY_BITS 19
 #define FB_RAY_MASK ((1u << FB_RAY_BITS) - 1u)
-#define FB_MAX_TAG ((1u << (32 - FB_RAY_BITS)) - 1u)
+#define FB_POS_BITS 11
+#define FB_POS_MASK ((1u << FB_POS_BITS) - 1u)
+#define FB_CLAIM_FRAME_SHIFT (FB_RAY_BITS + FB_POS_BITS)
+#define FB_MAX_CLAIM_FRAME 3u
+#define FB_MAX_OWNER_FRAME ((1u << (32 - FB_RAY_BITS)) - 1u)
+#define FB_MAX_ROUNDS 2000u
 #define FB_LIST_IDX_MASK 0x3fffffffu
 #define FB_CLS_COUNT 0u   // NORMAL voxel inside the update box: counted + stamp logic (Fiesta.h:248-275)
 #define FB_CLS_SKIP 1u    // len > max_ray_length or centre not in map: `continue` (Fiesta.h:245, 253)
@@ -58,7 +65,8 @@ struct FbCounters {
   unsigned n_changed[2];       // changed-tile lists by generation parity
   unsigned gen_stamp;          // monotonically increasing generation stamp for tile_flag dedupe
   unsigned generations;
-  unsigned ray_flag[3];        // "some reach changed" flags, rotating
+  unsigned ray_work[3];        // number of rays that have to walk in a round, rotating per round
+  unsigned ray_pad0;
   unsigned rays_cast, rays_dropped, ray_rounds, ray_error;
   unsigned long long ray_voxels;
   unsigned long long voxels_changed, voxels_reset, tile_visits;
@@ -124,14 +132,19 @@ struct FbRayArgs {
   double start[3];        // org / res
   double bmin[3], bmax[3];  // l_cornor/res, r_cornor/res
   double min_len, max_len;
+  int lattice_ok;         // host-verified: Pos2Vox((c+0.5)*res) == c - lattice_off for every DDA voxel c inside the box
+  int lattice_off[3];
   unsigned long long *cnt;
   uint32_t *stamp[2];
   uint32_t *touched;
   unsigned touched_cap;
-  uint32_t *ray_list;     // [cap][n] transposed, reversed (t = 0 is the voxel before the last emitted one)
+  uint32_t *ray_list;     // [n][cap] row-major, reversed (t = 0 is the voxel before the last emitted one)
   int *ray_len, *ray_reach;
+  unsigned *ray_act;      // per-round work list: rays that have to walk again
+  unsigned *ray_dirty;    // ray was displaced from a voxel by a lower ray since its last walk
   int cap;
-  unsigned tag_base;
+  unsigned frame_tag;     // claim frame tag (1..3)
+  unsigned owner_tag;     // endpoint-owner frame tag
   unsigned max_rounds;
   FbCounters *ctr;
 };

@@ -51,8 +51,8 @@ struct fiesta_map {
   // ray casting
   float *d_xyz; size_t cap_xyz;
   uint32_t *ray_list; size_t cap_ray_list;
-  int *ray_len, *ray_reach; size_t cap_rays;
-  unsigned tag_base;
+  int *ray_len, *ray_reach; unsigned *ray_act, *ray_dirty; size_t cap_rays;
+  unsigned frame_tag, owner_tag;
   // queries
   double *d_qin, *d_qout; size_t cap_q;
   cudaEvent_t ev[4];
@@ -61,7 +61,7 @@ struct fiesta_map {
 
 // ====================================================================== kernels
 __global__ void k_reset_ray_ctr(FbCounters *c) {
-  c->ray_flag[0] = c->ray_flag[1] = c->ray_flag[2] = 0;
+  c->ray_work[0] = c->ray_work[1] = c->ray_work[2] = 0u;
   c->rays_cast = c->rays_dropped = c->ray_rounds = c->ray_error = 0;
   c->ray_voxels = 0;
 }
@@ -284,7 +284,7 @@ void fiesta_destroy(fiesta_map *m) {
   if (m->stream) cudaStreamSynchronize(m->stream);
   void *dev[] = {m->cobs, m->cobs_b, m->stamp[0], m->stamp[1], m->occbits, m->occ, m->cnt, m->tile_flag, m->list[0], m->list[1],
                  m->changed[0], m->changed[1], m->changed_bbox[0], m->changed_bbox[1], m->touched, m->ins, m->del, m->d_ctr, m->d_ev,
-                 m->d_xyz, m->ray_list, m->ray_len, m->ray_reach, m->d_qin, m->d_qout};
+                 m->d_xyz, m->ray_list, m->ray_len, m->ray_reach, m->ray_act, m->ray_dirty, m->d_qin, m->d_qout};
   for (void *p : dev) if (p) cudaFree(p);
   if (m->h_ctr) cudaFreeHost(m->h_ctr);
   if (m->h_ev) cudaFreeHost(m->h_ev);
@@ -366,7 +366,7 @@ int fiesta_create(const fiesta_config *cfg, fiesta_map **out) {
   memset(m->h_ctr, 0, sizeof(FbCounters));
   m->h_ctr->gen_stamp = 1;
   CKD(cudaMemcpyAsync(m->d_ctr, m->h_ctr, sizeof(FbCounters), cudaMemcpyHostToDevice, m->stream));
-  m->tag_base = 1;
+  m->frame_tag = 0; m->owner_tag = 0;
   char err[256];
   if (fb_esdf_make_tensor_map(&m->tmap, g, m->cobs, err, sizeof(err)) != cudaSuccess) { set_error("%s", err); fiesta_destroy(m); return FIESTA_ERR_CUDA; }
   m->wf_blocks = fb_esdf_wavefront_blocks(m->device);
@@ -447,29 +447,55 @@ int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, co
     a.bmax[k] = m->r_cornor[k] / g.res;
   }
   a.min_len = p->min_ray_length; a.max_len = p->max_ray_length;
+  // Lattice fast path: the DDA walks floor(world/res) voxels while the map uses floor((world-origin)/res) (ESDFMap.cpp:74-77).
+  // If, for every DDA coordinate c inside the box and every axis, the voxel centre (c+0.5)*res lies in the map and maps to
+  // c - off (checked here with the reference's own fp64 expressions), the per-voxel divisions can be skipped exactly.
+  a.lattice_ok = 1;
+  for (int k = 0; k < 3 && a.lattice_ok; ++k) {
+    const int G = k == 0 ? g.gx : (k == 1 ? g.gy : g.gz);
+    const long long clo = (long long)ceil(a.bmin[k]), chi = (long long)ceil(a.bmax[k]);   // integers c with bmin <= c < bmax
+    if (chi - clo > 4096 || chi <= clo) { a.lattice_ok = 0; break; }
+    const double c0 = ((double)clo + 0.5) * g.res;
+    const long long off = clo - (long long)floor((c0 - g.origin[k]) / g.res);
+    a.lattice_off[k] = (int)off;
+    for (long long c = clo; c < chi; ++c) {
+      const double ctr = ((double)c + 0.5) * g.res;
+      const long long v = (long long)floor((ctr - g.origin[k]) / g.res);
+      if (ctr < g.min_range[k] || ctr > g.max_range[k] || v != c - off || v < 0 || v >= G) { a.lattice_ok = 0; break; }
+    }
+  }
   double capd = ceil(1.7320508075688772 * (p->max_ray_length / g.res)) + 8.0;
   if (!(capd < 1500.0)) capd = 1500.0;
   if (capd < 1.0) capd = 1.0;
   a.cap = (int)capd;
-  a.max_rounds = 1000;
-  if (m->tag_base + a.max_rounds + 2 > FB_MAX_TAG) {                      // stamp tags exhausted: clear and restart
+  a.max_rounds = FB_MAX_ROUNDS;
+  if (m->frame_tag >= FB_MAX_CLAIM_FRAME) {                               // claim frame tags exhausted: clear and restart
     CK(cudaMemsetAsync(m->stamp[0], 0, (size_t)g.ptotal * 4, m->stream));
-    CK(cudaMemsetAsync(m->stamp[1], 0, (size_t)g.ptotal * 4, m->stream));
-    m->tag_base = 1;
+    m->frame_tag = 0;
   }
-  a.tag_base = m->tag_base;
+  if (m->owner_tag >= FB_MAX_OWNER_FRAME) {
+    CK(cudaMemsetAsync(m->stamp[1], 0, (size_t)g.ptotal * 4, m->stream));
+    m->owner_tag = 0;
+  }
+  a.frame_tag = ++m->frame_tag;
+  a.owner_tag = ++m->owner_tag;
   int r;
   size_t need_rays = (size_t)n;
   if (need_rays > m->cap_rays) {
-    size_t c1 = m->cap_rays, c2 = m->cap_rays;
+    size_t c1 = m->cap_rays, c2 = m->cap_rays, c3 = m->cap_rays, c4 = m->cap_rays;
     if ((r = ensure(&m->ray_len, &c1, need_rays, false, m->stream))) return r;
     if ((r = ensure(&m->ray_reach, &c2, need_rays, false, m->stream))) return r;
-    m->cap_rays = c1 < c2 ? c1 : c2;
+    if ((r = ensure(&m->ray_act, &c3, need_rays, false, m->stream))) return r;
+    if ((r = ensure(&m->ray_dirty, &c4, need_rays, false, m->stream))) return r;
+    m->cap_rays = c1;
+    if (c2 < m->cap_rays) m->cap_rays = c2;
+    if (c3 < m->cap_rays) m->cap_rays = c3;
+    if (c4 < m->cap_rays) m->cap_rays = c4;
   }
   if ((r = ensure(&m->ray_list, &m->cap_ray_list, (size_t)a.cap * (size_t)n, false, m->stream))) return r;
   a.cnt = m->cnt; a.stamp[0] = m->stamp[0]; a.stamp[1] = m->stamp[1];
   a.touched = m->touched; a.touched_cap = (unsigned)(g.ptotal > 0xffffffffLL ? 0xffffffffu : (unsigned)g.ptotal);
-  a.ray_list = m->ray_list; a.ray_len = m->ray_len; a.ray_reach = m->ray_reach; a.ctr = m->d_ctr;
+  a.ray_list = m->ray_list; a.ray_len = m->ray_len; a.ray_reach = m->ray_reach; a.ray_act = m->ray_act; a.ray_dirty = m->ray_dirty; a.ctr = m->d_ctr;
   CK(cudaEventRecord(m->ev[0], m->stream));
   k_reset_ray_ctr<<<1, 1, 0, m->stream>>>(m->d_ctr);
   int launches = 1;
@@ -478,7 +504,6 @@ int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, co
   CK(cudaEventRecord(m->ev[1], m->stream));
   if ((r = fetch_counters(m))) return r;
   CK(cudaEventElapsedTime(&m->st.ms_raycast, m->ev[0], m->ev[1]));
-  m->tag_base += m->h_ctr->ray_rounds + 1;
   m->st.rays_cast = m->h_ctr->rays_cast; m->st.rays_dropped = m->h_ctr->rays_dropped;
   m->st.ray_voxels = (int64_t)m->h_ctr->ray_voxels; m->st.raycast_rounds = m->h_ctr->ray_rounds;
   m->st.touched_voxels = m->n_touched;

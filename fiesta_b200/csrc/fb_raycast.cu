@@ -13,14 +13,16 @@
 //                     tagged stamp) == the set_occ_ dedupe.
 //   k_ray_trace     : per surviving ray (one thread each; the DDA's tMax += tDelta recurrence is sequential fp64 and
 //                     must round exactly like the reference): Amanatides-Woo traversal with the reference's quirks
-//                     (direction from integer voxel deltas, tie order z>y>x, corner-based distance cut), run twice:
-//                     count, then write the voxel list back-to-front, transposed ([step][ray]) so a warp reads
-//                     contiguous memory.
-//   k_ray_resolve   : persistent cooperative kernel.  Round r: every ray walks its list from the far end and stops at the
-//                     first voxel whose round r-1 stamp belongs to a lower ray index, stamping what it passes with
-//                     atomicMax(tag|~ray) into the round-r array.  Rays with lower indices than everything they meet are
-//                     exact after round 1, and by induction on the ray index the iteration reaches the unique fixpoint =
-//                     the serial result; it stops when no ray's reach changed.  A last walk adds the counts.
+//                     (direction from integer voxel deltas, tie order z>y>x, corner-based distance cut); every pushed voxel
+//                     is classified (count / skip / stop / stamp-only) and stored in the ray's row.
+//   k_ray_resolve   : persistent cooperative kernel, event driven, one WARP per walking ray.  Every voxel holds a claim word {ray, position in
+//                     that ray's list}; a claim is VALID while position < the claiming ray's current reach.  In a round every
+//                     not-yet-final ray walks its list from the far end 32 voxels at a time, stops at the first voxel validly
+//                     claimed by a LOWER ray index and claims (atomicCAS) what it passes.  Claims are updated in place, so
+//                     higher rays see what lower rays did; a ray that displaces a higher ray's claim marks it dirty.  After
+//                     the first full pass a ray walks again only if it is dirty or the claim that stopped it became
+//                     invalid -- otherwise its walk would give the same result.  A ray only depends on lower indices, so by
+//                     induction the only state in which no ray has to walk is the serial result.  A last walk adds the counts.
 // All fp64 arithmetic is written in the reference's operation order and the library is compiled with -fmad=false.
 #include <cooperative_groups.h>
 #include "fb_common.cuh"
@@ -99,7 +101,7 @@ __global__ void k_ray_endpoints(FbGeom g, FbRayArgs a) {
       if (fb_resolve_vox(g, vx, vy, vz, ii, in_range)) {
         if (in_range) fb_count(a, ii, kind == 1 ? 1u : 0u);
         // set_occ_ ownership: lowest point index wins (Fiesta.h:227-230)
-        atomicMax(&a.stamp[1][ii], (a.tag_base << FB_RAY_BITS) | (FB_RAY_MASK - (unsigned)i));
+        atomicMax(&a.stamp[1][ii], (a.owner_tag << FB_RAY_BITS) | (FB_RAY_MASK - (unsigned)i));
       }
     }
   }
@@ -165,17 +167,15 @@ __device__ __forceinline__ int fb_dda_walk(FbDda d, const FbRayArgs &a, F emit) 
   return n;
 }
 
-// pass 0: count + ownership check; pass 1: write the list.
-template <int PASS>
+// One thread per point: ownership check (set_occ_ dedupe), then the DDA; every pushed voxel is classified and stored in
+// the ray's row in forward order.  The walk back-to-front in k_ray_resolve reads row[L-1-t].
 __global__ void k_ray_trace(FbGeom g, FbRayArgs a) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
-  int len = a.ray_len[i];
-  if (PASS == 0 ? (len < 0) : (len <= 0)) return;
+  if (a.ray_len[i] < 0) return;                               // point skipped by the gating in k_ray_endpoints
   double px, py, pz;
-  const int kind = fb_endpoint(a, i, px, py, pz);
-  (void)kind;
-  if (PASS == 0) {
+  fb_endpoint(a, i, px, py, pz);
+  {
     int vx, vy, vz;
     if (fb_pos_to_vox(g, px, py, pz, vx, vy, vz)) {
       long long ii; bool in_range;
@@ -187,96 +187,174 @@ __global__ void k_ray_trace(FbGeom g, FbRayArgs a) {
   }
   FbDda d;
   const bool moving = fb_dda_init(d, a.start, px / g.res, py / g.res, pz / g.res);
-  if (PASS == 0) {
-    int n = 0;
-    if (moving) n = fb_dda_walk(d, a, [](int, int, int, int) {});
-    atomicAdd(&a.ctr->rays_cast, 1u);
-    if (n < 0) { atomicAdd(&a.ctr->rays_dropped, 1u); if (n == -1) atomicExch(&a.ctr->ray_error, 1u); n = 0; }
-    int L = n > 0 ? n - 1 : 0;                                // `for (i = output.size() - 2; ...)`: the last voxel is skipped
-    if (L > a.cap) { L = 0; atomicExch(&a.ctr->ray_error, 2u); atomicAdd(&a.ctr->rays_dropped, 1u); }
-    a.ray_len[i] = L;
-    a.ray_reach[i] = -1;
-    if (L) atomicAdd(&a.ctr->ray_voxels, (unsigned long long)L);
-  } else {
-    const int L = len;
-    fb_dda_walk(d, a, [&](int x, int y, int z, int j) {
-      if (j >= L) return;                                     // the last pushed voxel is never visited (Fiesta.h:239)
+  uint32_t *row = a.ray_list + i * a.cap;
+  int n = 0;
+  if (moving)
+    n = fb_dda_walk(d, a, [&](int x, int y, int z, int j) {
+      if (j >= a.cap) return;
       const double cx = (x + 0.5) * g.res, cy = (y + 0.5) * g.res, cz = (z + 0.5) * g.res;   // Fiesta.h:240
       const double l = fb_norm3(cx, cy, cz, a.org);
       unsigned e;
       if (l < a.min_len) e = FB_CLS_STOP << 30;
       else if (l > a.max_len) e = FB_CLS_SKIP << 30;
-      else {
+      else if (a.lattice_ok) {                                // host-verified: map voxel = DDA voxel - offset, always in map
+        const int vx = x - a.lattice_off[0], vy = y - a.lattice_off[1], vz = z - a.lattice_off[2];
+        e = ((fb_in_range(g, vx, vy, vz) ? FB_CLS_COUNT : FB_CLS_STAMP) << 30) | (unsigned)fb_ii(g, vx, vy, vz);
+      } else {
         int vx, vy, vz; long long ii; bool in_range;
         if (fb_pos_to_vox(g, cx, cy, cz, vx, vy, vz) && fb_resolve_vox(g, vx, vy, vz, ii, in_range))
           e = ((in_range ? FB_CLS_COUNT : FB_CLS_STAMP) << 30) | (unsigned)ii;
         else e = FB_CLS_SKIP << 30;                           // SetOccupancy returned -10000 (Fiesta.h:253)
       }
-      a.ray_list[(long long)(L - 1 - j) * a.n + i] = e;
+      row[j] = e;
     });
-  }
+  atomicAdd(&a.ctr->rays_cast, 1u);
+  if (n < 0) { atomicAdd(&a.ctr->rays_dropped, 1u); if (n == -1) atomicExch(&a.ctr->ray_error, 1u); n = 0; }
+  int L = n > 0 ? n - 1 : 0;                                  // `for (i = output.size() - 2; ...)`: the last voxel is skipped
+  if (L > a.cap) { L = 0; atomicExch(&a.ctr->ray_error, 2u); atomicAdd(&a.ctr->rays_dropped, 1u); }
+  a.ray_len[i] = L;
+  a.ray_reach[i] = L;                                         // optimistic: claims made while walking count as valid
+  if (L) atomicAdd(&a.ctr->ray_voxels, (unsigned long long)L);
 }
 
 // ---------------------------------------------------------------- stamp resolution + counting
-__global__ void __launch_bounds__(256) k_ray_resolve(FbGeom g, FbRayArgs a) {
-  cg::grid_group grid = cg::this_grid();
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long nthreads = (long long)gridDim.x * blockDim.x;
-  unsigned round = 1;
-  for (;; ++round) {
-    const unsigned tag = a.tag_base + round, oldtag = tag - 1u;
-    const uint32_t *so = a.stamp[(round - 1u) & 1u];
-    uint32_t *sn = a.stamp[round & 1u];
-    bool changed = false;
-    for (long long i = tid; i < a.n; i += nthreads) {
-      const int L = a.ray_len[i];
-      if (L <= 0) continue;
-      const unsigned me = (unsigned)i;
-      int t = 0;
-      for (; t < L; ++t) {
-        const unsigned e = __ldcg(&a.ray_list[(long long)t * a.n + i]);
-        const unsigned cls = e >> 30;
-        if (cls == FB_CLS_STOP) break;
-        if (cls == FB_CLS_SKIP) continue;
-        const unsigned ii = e & FB_LIST_IDX_MASK;
-        const unsigned o = __ldcg(&so[ii]);
-        if ((o >> FB_RAY_BITS) == oldtag && (FB_RAY_MASK - (o & FB_RAY_MASK)) < me) break;   // set_free_[idx] == tt by an earlier ray
-        atomicMax(&sn[ii], (tag << FB_RAY_BITS) | (FB_RAY_MASK - me));
-      }
-      if (t != a.ray_reach[i]) { a.ray_reach[i] = t; changed = true; }
+// One warp per ray.  reach[i] = index at which the back-walk stops (L if it runs off the list) | FB_REACH_BLOCKED when it
+// stopped at a voxel stamped by an earlier ray (that voxel is still counted, Fiesta.h:248-268).
+#define FB_REACH_BLOCKED 0x40000000
+
+// Is the voxel whose claim word is `seen` validly claimed by a ray with a lower index than `i`?
+__device__ __forceinline__ bool fb_claim_blocks(const FbRayArgs &a, unsigned seen, unsigned i) {
+  if ((seen >> FB_CLAIM_FRAME_SHIFT) != a.frame_tag) return false;                       // claim of an older frame
+  const unsigned j = (seen >> FB_POS_BITS) & FB_RAY_MASK, tj = seen & FB_POS_MASK;
+  return j < i && (int)tj < (__ldcg(&a.ray_reach[j]) & ~FB_REACH_BLOCKED);               // set_free_[idx] == tt by an EARLIER ray
+}
+
+// One warp walks ray i from the far end: stops at the first voxel validly claimed by a lower ray (or at the
+// min_ray_length class), claims what it passes and marks every higher ray it displaces dirty.  Returns the new reach.
+__device__ __forceinline__ int fb_walk_ray(const FbRayArgs &a, unsigned i, unsigned lane) {
+  uint32_t *claims = a.stamp[0];
+  const unsigned fr = a.frame_tag << FB_CLAIM_FRAME_SHIFT;
+  const int L = a.ray_len[i];
+  const uint32_t *row = a.ray_list + (long long)i * a.cap;
+  int result = L;
+  for (int t0 = 0; t0 < L; t0 += 32) {
+    const int t = t0 + (int)lane;
+    unsigned e = (FB_CLS_SKIP << 30);
+    if (t < L) e = __ldcg(&row[L - 1 - t]);
+    const unsigned cls = e >> 30, ii = e & FB_LIST_IDX_MASK;
+    const bool normal = cls == FB_CLS_COUNT || cls == FB_CLS_STAMP;
+    const unsigned mine = fr | (i << FB_POS_BITS) | (unsigned)t;
+    int st = 0;                           // 0 = passable & already mine, 1 = passable & must be claimed, 2 = blocked
+    unsigned seen = 0;
+    if (normal) {
+      seen = __ldcg(&claims[ii]);
+      if (seen != mine) st = fb_claim_blocks(a, seen, i) ? 2 : 1;
     }
-    if (changed) atomicExch(&a.ctr->ray_flag[round % 3u], 1u);
+    const unsigned m = __ballot_sync(0xffffffffu, st == 2 || cls == FB_CLS_STOP);
+    const int first = m ? (__ffs(m) - 1) : 32;
+    while (st == 1 && (int)lane < first) {                    // claim; a failed CAS means someone else wrote: look again
+      const unsigned old = atomicCAS(&claims[ii], seen, mine);
+      if (old == seen) {
+        st = 0;
+        if ((old >> FB_CLAIM_FRAME_SHIFT) == a.frame_tag) {   // displaced a (higher) ray: it has to walk again
+          const unsigned k = (old >> FB_POS_BITS) & FB_RAY_MASK;
+          if (k != i) { __threadfence(); a.ray_dirty[k] = 1u; }
+        }
+        break;
+      }
+      seen = old;
+      if (seen == mine) { st = 0; break; }
+      if (fb_claim_blocks(a, seen, i)) { st = 2; break; }
+    }
+    const unsigned m2 = __ballot_sync(0xffffffffu, st == 2 || cls == FB_CLS_STOP);
+    if (m2) {
+      const int f2 = __ffs(m2) - 1;
+      const bool by_stamp = __shfl_sync(0xffffffffu, st == 2 ? 1 : 0, f2) != 0;
+      result = (t0 + f2) | (by_stamp ? FB_REACH_BLOCKED : 0);
+      break;
+    }
+  }
+  return result;
+}
+
+#define RR_THREADS 1024
+#define RR_WARPS (RR_THREADS / 32)
+__global__ void __launch_bounds__(RR_THREADS, 1) k_ray_resolve(FbGeom g, FbRayArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  const unsigned gw = blockIdx.x * RR_WARPS + wib, nwarps = gridDim.x * RR_WARPS;
+  const unsigned gt = blockIdx.x * RR_THREADS + threadIdx.x, nthreads = gridDim.x * RR_THREADS;
+  const uint32_t *claims = a.stamp[0];
+
+  // Event-driven rounds.  Each round: (check) one thread per cast ray decides whether the ray has to walk again: it was
+  // displaced by a lower ray (dirty), or the claim that stopped it is no longer valid; (walk) one warp per listed ray.
+  // A ray whose claims are intact and whose blocker is still valid would walk to exactly the same result, so skipping it
+  // is exact.  Round 1 walks everything.  The loop ends when a check finds nothing to do.
+  unsigned round = 0;
+  for (;;) {
+    ++round;
+    unsigned *work_n = &a.ctr->ray_work[round % 3u];
+    for (long long i = gt; i < a.n; i += nthreads) {
+      const int L = a.ray_len[i];
+      bool need = false;
+      if (L > 0) {
+        if (round == 1u || a.ray_dirty[i]) need = true;
+        else {
+          const int rr = a.ray_reach[i];
+          if (rr & FB_REACH_BLOCKED) {
+            const unsigned e = __ldcg(&a.ray_list[i * a.cap + (L - 1 - (rr & ~FB_REACH_BLOCKED))]);
+            need = !fb_claim_blocks(a, __ldcg(&claims[e & FB_LIST_IDX_MASK]), (unsigned)i);
+          }
+        }
+      }
+      const unsigned slot = fb_warp_append(work_n, need);
+      if (need) { a.ray_act[slot] = (unsigned)i; a.ray_dirty[i] = 0u; }
+    }
     grid.sync();
-    const unsigned any = __ldcg(&a.ctr->ray_flag[round % 3u]);
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.ctr->ray_flag[(round + 2u) % 3u] = 0u;   // next used two barriers from now
-    if (!any || round >= a.max_rounds) break;
+    const unsigned nw = __ldcg(work_n);
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.ctr->ray_work[(round + 2u) % 3u] = 0u;   // next used two barriers from now
+    if (nw == 0u || round >= a.max_rounds) break;
+    for (unsigned p = gw; p < nw; p += nwarps) {
+      const unsigned i = __ldcg(&a.ray_act[p]);
+      const int result = fb_walk_ray(a, i, lane);
+      if (lane == 0) a.ray_reach[i] = result;
+    }
+    grid.sync();
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.ctr->ray_rounds = round;
     if (round >= a.max_rounds) a.ctr->ray_error = 3u;
   }
-  // final walk: `SetOccupancy(tmp, 0)` for every visited voxel, including the one that stops the walk (Fiesta.h:248-268)
-  const unsigned tag = a.tag_base + round;
-  const uint32_t *sf = a.stamp[round & 1u];
-  for (long long i = tid; i < a.n; i += nthreads) {
+  // ---- counts: SetOccupancy(tmp, 0) for every visited voxel, including the one that stopped the walk (Fiesta.h:248-268)
+  for (long long i = gw; i < a.n; i += nwarps) {
     const int L = a.ray_len[i];
-    const unsigned me = (unsigned)i;
-    for (int t = 0; t < L; ++t) {
-      const unsigned e = __ldcg(&a.ray_list[(long long)t * a.n + i]);
-      const unsigned cls = e >> 30;
-      if (cls == FB_CLS_STOP) break;
-      if (cls == FB_CLS_SKIP) continue;
-      const unsigned ii = e & FB_LIST_IDX_MASK;
-      if (cls == FB_CLS_COUNT) fb_count(a, ii, 0u);
-      const unsigned o = __ldcg(&sf[ii]);
-      if ((o >> FB_RAY_BITS) == tag && (FB_RAY_MASK - (o & FB_RAY_MASK)) < me) break;
+    if (L <= 0) continue;
+    const int rr = a.ray_reach[i];
+    const int R = (rr & ~FB_REACH_BLOCKED) + ((rr & FB_REACH_BLOCKED) ? 1 : 0);
+    const uint32_t *row = a.ray_list + (long long)i * a.cap;
+    for (int t0 = 0; t0 < R; t0 += 32) {
+      const int t = t0 + (int)lane;
+      bool cnt = false; unsigned ii = 0;
+      if (t < R) { const unsigned e = __ldcg(&row[L - 1 - t]); cnt = (e >> 30) == FB_CLS_COUNT; ii = e & FB_LIST_IDX_MASK; }
+      bool first = false;
+      if (cnt) {
+        const unsigned long long old = atomicAdd(&a.cnt[ii], 1ull);
+        first = (unsigned)(old & 0xffffffffull) == 0u;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, first);
+      if (m) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&a.ctr->n_touched, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (first) a.touched[base + __popc(m & ((1u << lane) - 1u))] = ii;
+      }
     }
   }
 }
 
 int fb_ray_resolve_blocks(int device) {
   int per_sm = 0, sms = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ray_resolve, 256, 0) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ray_resolve, RR_THREADS, 0) != cudaSuccess) return 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   return per_sm * sms;
 }
@@ -285,15 +363,13 @@ cudaError_t fb_ray_frame(const FbGeom &g, const FbRayArgs &a, int nblocks_resolv
   if (a.n <= 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((a.n + 127) / 128);
   k_ray_endpoints<<<blocks, 128, 0, s>>>(g, a);
-  k_ray_trace<0><<<blocks, 128, 0, s>>>(g, a);
-  k_ray_trace<1><<<blocks, 128, 0, s>>>(g, a);
+  k_ray_trace<<<blocks, 128, 0, s>>>(g, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  long long want = (a.n + 255) / 256;
-  int nb = (int)(want < nblocks_resolve ? want : nblocks_resolve);
+  int nb = nblocks_resolve;
   if (nb < 1) nb = 1;
   void *args[] = {(void *)&g, (void *)&a};
-  e = cudaLaunchCooperativeKernel((void *)k_ray_resolve, dim3(nb), dim3(256), args, 0, s);
-  if (launches) *launches += 4;
+  e = cudaLaunchCooperativeKernel((void *)k_ray_resolve, dim3(nb), dim3(RR_THREADS), args, 0, s);
+  if (launches) *launches += 3;
   return e;
 }
