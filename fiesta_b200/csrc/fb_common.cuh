@@ -13,6 +13,8 @@
 //   cnt    u64   {num_hit_:32 | num_miss_(=all observations):32} so one 64-bit atomicAdd counts an event (ESDFMap.cpp:424-425).
 //   stamp  2xu32 per-frame ray stamps, the device form of Fiesta's set_free_/set_occ_ (Fiesta.h:60-64,107-110).
 //   occbit u32/32 voxels  Exist() bitmap (ESDFMap.cpp:16-22), kept L2-resident for the dependant scan.
+// The occupancy queue (occupancy_queue_, ESDFMap.h:96) is kept at 8^3-tile granularity: the first observation of a voxel
+// since the last integration marks its tile; UpdateOccupancy then streams the counters of the marked tiles.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -60,9 +62,11 @@ struct FbGeom {
 };
 
 struct FbCounters {
-  unsigned n_touched, n_ins, n_del;
+  unsigned n_touched, n_ins, n_del;   // n_touched: voxels integrated by the last UpdateOccupancy
+  unsigned n_touch_tiles;      // tiles holding pending observations (the occupancy queue)
   unsigned n_list[2];          // active-tile work lists (ping-pong)
   unsigned n_changed[2];       // changed-tile lists by generation parity
+  unsigned next_work[4];       // dynamic tile fetch counters: [phase1 even, phase1 odd, phase2 even, phase2 odd]
   unsigned gen_stamp;          // monotonically increasing generation stamp for tile_flag dedupe
   unsigned generations;
   unsigned ray_work[3];        // number of rays that have to walk in a round, rotating per round
@@ -70,7 +74,7 @@ struct FbCounters {
   unsigned rays_cast, rays_dropped, ray_rounds, ray_error;
   unsigned long long ray_voxels;
   unsigned long long voxels_changed, voxels_reset, tile_visits;
-  unsigned pad[2];
+  unsigned pad[1];
 };
 
 __host__ __device__ __forceinline__ uint32_t fb_pack(int x, int y, int z) {
@@ -111,17 +115,39 @@ __device__ __forceinline__ unsigned fb_warp_append(unsigned *counter, bool pred)
 }
 #endif
 
+#ifdef __CUDACC__
+struct FbTouch {
+  unsigned long long *cnt;
+  uint32_t *touch_flag, *touch_list;
+  unsigned epoch;
+  FbCounters *ctr;
+};
+// One observation of voxel ii (ESDFMap.cpp:424-435): num_miss_++, num_hit_ += occ; the first one since the last
+// integration (num_miss_ == 1) queues the voxel -- here: marks its 8^3 tile.
+__device__ __forceinline__ void fb_touch(const FbGeom &g, const FbTouch &t, unsigned ii, unsigned occ) {
+  const unsigned long long old = atomicAdd(&t.cnt[ii], ((unsigned long long)occ << 32) | 1ull);
+  if ((unsigned)(old & 0xffffffffull) == 0u) {
+    const unsigned z = ii % (unsigned)g.pz, xy = ii / (unsigned)g.pz, y = xy % (unsigned)g.gy, x = xy / (unsigned)g.gy;
+    const unsigned tile = ((x >> 3) * g.ty + (y >> 3)) * g.tz + (z >> 3);
+    if (__ldcg(&t.touch_flag[tile]) != t.epoch && atomicExch(&t.touch_flag[tile], t.epoch) != t.epoch)
+      t.touch_list[atomicAdd(&t.ctr->n_touch_tiles, 1u)] = tile;
+  }
+}
+#endif
+
 // ---- host-side launch interface (defined in fb_esdf.cu / fb_raycast.cu) ----
 struct FbEsdfArgs {
   uint32_t *cobs, *cobs_b;
   const double *occ;
   const uint32_t *occbits;
-  uint32_t *tile_flag;
+  uint32_t *tile_flag;   // generation stamp for which a tile is queued (dedupe)
+  uint32_t *nb_flag;     // generation stamp for which a NEIGHBOUR (or a seed/reset) queued the tile: real work to do
   uint32_t *list[2];
   uint32_t *changed[2];
   uint32_t *changed_bbox[2];
   FbCounters *ctr;
   double l_occ;
+  unsigned long long *dbg;   // optional per-generation trace: {nwork, nchanged, t_phase1_ns, t_phase2_ns} x 256 (FIESTA_DEBUG_WF=1)
 };
 
 struct FbRayArgs {
@@ -136,8 +162,8 @@ struct FbRayArgs {
   int lattice_off[3];
   unsigned long long *cnt;
   uint32_t *stamp[2];
-  uint32_t *touched;
-  unsigned touched_cap;
+  uint32_t *touch_flag, *touch_list;
+  unsigned touch_epoch;
   uint32_t *ray_list;     // [n][cap] row-major, reversed (t = 0 is the voxel before the last emitted one)
   int *ray_len, *ray_reach;
   unsigned *ray_act;      // per-round work list: rays that have to walk again

@@ -30,7 +30,8 @@ namespace cg = cooperative_groups;
 __device__ __forceinline__ unsigned ld_cg_u32(const unsigned *p) { return __ldcg(p); }
 
 // Queue tile t for the generation identified by `stamp` (dedupe through tile_flag).
-__device__ __forceinline__ void fb_activate(const FbEsdfArgs &a, unsigned t, unsigned stamp, int which) {
+__device__ __forceinline__ void fb_activate(const FbEsdfArgs &a, unsigned t, unsigned stamp, int which, bool work = true) {
+  if (work) a.nb_flag[t] = stamp;
   if (atomicExch(&a.tile_flag[t], stamp) != stamp) {
     unsigned slot = atomicAdd(&a.ctr->n_list[which], 1u);
     a.list[which][slot] = t;
@@ -122,6 +123,10 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
   __shared__ __align__(128) uint32_t buf[2][FB_BOX_WORDS];
   __shared__ __align__(8) uint64_t mbar;
   __shared__ int s_bbox[6];
+  __shared__ unsigned s_w;
+  // per z-row bit masks of the FRESH flags (bit = box z index), one set per relaxation buffer: lets a voxel find out with
+  // 13 loads whether anything within reach is in the queue before it pays for the 24-neighbour evaluation
+  __shared__ uint32_t fmask[2][FB_BOX * FB_BOX];
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   const int lx = tid >> 6, ly = (tid >> 3) & 7, lz = tid & 7;
@@ -142,14 +147,37 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
   for (;;) {
     const unsigned nwork = ld_cg_u32(&a.ctr->n_list[cur]);
     if (nwork == 0) break;
+    unsigned long long t_a = 0;
+    if (a.dbg && blockIdx.x == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
     const unsigned par = gen & 1u;
     if (blockIdx.x == 0 && tid == 0) a.ctr->n_changed[par ^ 1u] = 0;   // last read two barriers ago
 
-    // ---------------- phase 1: relax every active tile against the previous generation
-    for (unsigned w = blockIdx.x; w < nwork; w += gridDim.x) {
+    // ---------------- phase 1: relax every active tile against the previous generation (tiles fetched dynamically)
+    if (blockIdx.x == 0 && tid == 0) { a.ctr->next_work[par ^ 1u] = 0; a.ctr->next_work[2u + (par ^ 1u)] = 0; }
+    const unsigned stamp_cur = stamp0 + gen;
+    for (;;) {
+      if (tid == 0) s_w = atomicAdd(&a.ctr->next_work[par], 1u);
+      __syncthreads();
+      const unsigned w = s_w;
+      __syncthreads();
+      if (w >= nwork) break;
       const unsigned tile = ld_cg_u32(&a.list[cur][w]);
       const int tzc = tile % g.tz, tyc = (tile / g.tz) % g.ty, txc = tile / (g.tz * g.ty);
       const int x0 = txc * FB_TILE, y0 = tyc * FB_TILE, z0 = tzc * FB_TILE;
+      if (ld_cg_u32(&a.nb_flag[tile]) != stamp_cur) {
+        // Queued only by itself: nothing within reach changed since its local fixpoint, so its FRESH voxels would pull the
+        // same values again.  Just retire the flags (through the staging grid, so that neighbours relaxing in this very
+        // generation still see them).
+        const int vx = x0 + lx, vy = y0 + ly, vz = z0 + lz;
+        if (fb_in_grid(g, vx, vy, vz)) { const long long ii = fb_ii(g, vx, vy, vz); a.cobs_b[ii] = __ldcg(&a.cobs[ii]) & FB_CODE_MASK; }
+        if (tid == 0) {
+          ++my_visits;
+          const unsigned slot = atomicAdd(&a.ctr->n_changed[par], 1u);
+          a.changed[par][slot] = tile;
+          a.changed_bbox[par][slot] = 0u;
+        }
+        continue;
+      }
       if (tid == 0) {
         s_bbox[0] = s_bbox[2] = s_bbox[4] = 8; s_bbox[1] = s_bbox[3] = s_bbox[5] = -1;
         mbar_expect_tx(&mbar, FB_BOX_WORDS * 4);
@@ -160,6 +188,12 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
       const int vx = x0 + lx, vy = y0 + ly, vz = z0 + lz;
       const uint32_t orig = buf[0][s];
       for (int k = tid; k < FB_BOX_WORDS; k += WF_THREADS) buf[1][k] = buf[0][k];   // halo must exist in both buffers
+      if (tid < FB_BOX * FB_BOX) {                            // FRESH mask of every z-row of the box (halo bits never change)
+        uint32_t mk = 0;
+#pragma unroll
+        for (int z = 0; z < FB_BOXZ; ++z) mk |= (buf[0][tid * FB_BOXZ + z] >> 31) << z;
+        fmask[0][tid] = mk; fmask[1][tid] = mk;
+      }
       // A voxel relaxes iff it has been observed (unknown voxels are barriers: distance_ = -10000 is never > tmp,
       // ESDFMap.cpp:382) and lies inside the update box (only in-box voxels are ever queued, ESDFMap.cpp:351,378).
       const uint32_t ocode = orig & FB_CODE_MASK;
@@ -177,7 +211,17 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
       int cb = 0;
       for (;;) {
         uint32_t best = mine;
+        bool active = false;
         if (updatable) {
+          const uint32_t *fm = fmask[cb];
+          const int r = (lx + FB_HALO) * FB_BOX + (ly + FB_HALO), zb = lz + FB_ZPAD;
+          uint32_t any5 = (fm[r] >> (zb - 2)) & 0x1fu;                                   // self, z+-1, z+-2
+          uint32_t any3 = ((fm[r - FB_BOX] | fm[r + FB_BOX] | fm[r - 1] | fm[r + 1]) >> (zb - 1)) & 7u;   // x+-1 / y+-1 rows: z-1..z+1
+          uint32_t any1 = ((fm[r - FB_BOX - 1] | fm[r - FB_BOX + 1] | fm[r + FB_BOX - 1] | fm[r + FB_BOX + 1] |
+                            fm[r - 2 * FB_BOX] | fm[r + 2 * FB_BOX] | fm[r - 2] | fm[r + 2]) >> zb) & 1u;   // planar diagonals and +-2 steps
+          active = (any5 | any3 | any1) != 0u;
+        }
+        if (active) {
           unsigned bestd = 0xffffffffu;
           if (mine >= 2u) { int ox, oy, oz; fb_unpack(mine, ox, oy, oz); ox -= vx; oy -= vy; oz -= vz; bestd = (unsigned)(ox * ox + oy * oy + oz * oz); }
           const uint32_t *b = buf[cb];
@@ -196,6 +240,14 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
         }
         fresh = best != mine ? 1u : 0u;
         buf[cb ^ 1][s] = best | (fresh << 31);
+        {                                                     // a warp owns 4 interior z-rows: lanes 8r..8r+7 = row (lx, ly0 + r)
+          const uint32_t bal = __ballot_sync(0xffffffffu, fresh != 0u);
+          const int lane = tid & 31;
+          if (lane < 4) {
+            const int r = (lx + FB_HALO) * FB_BOX + (((tid >> 5) & 1) * 4 + lane + FB_HALO);
+            fmask[cb ^ 1][r] = (fmask[cb][r] & ~(0xffu << FB_ZPAD)) | (((bal >> (8 * lane)) & 0xffu) << FB_ZPAD);
+          }
+        }
         const int any = __syncthreads_or((int)fresh);
         mine = best;
         cb ^= 1;
@@ -228,11 +280,18 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
     }
     grid.sync();
 
+    unsigned long long t_b = 0;
+    if (a.dbg && blockIdx.x == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_b));
     // ---------------- phase 2: commit changed tiles, activate their neighbours for the next generation
     if (blockIdx.x == 0 && tid == 0) a.ctr->n_list[cur] = 0;    // consumed; becomes the append target two phases from now
     const unsigned nchg = ld_cg_u32(&a.ctr->n_changed[par]);
     const unsigned stamp = stamp0 + gen + 1u;
-    for (unsigned w = blockIdx.x; w < nchg; w += gridDim.x) {
+    for (;;) {
+      if (tid == 0) s_w = atomicAdd(&a.ctr->next_work[2u + par], 1u);
+      __syncthreads();
+      const unsigned w = s_w;
+      __syncthreads();
+      if (w >= nchg) break;
       const unsigned tile = ld_cg_u32(&a.changed[par][w]);
       const unsigned bb = ld_cg_u32(&a.changed_bbox[par][w]);
       const int tzc = tile % g.tz, tyc = (tile / g.tz) % g.ty, txc = tile / (g.tz * g.ty);
@@ -244,7 +303,7 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
       if (tid < 27 && (bb >> 18)) {                            // some record changed: its new value must reach the neighbours
         const int ox = tid / 9 - 1, oy = (tid / 3) % 3 - 1, oz = tid % 3 - 1;
         const int nz = (ox != 0) + (oy != 0) + (oz != 0);
-        if (nz == 0) fb_activate(a, tile, stamp, (int)(cur ^ 1u));   // revisit once more to clear the FRESH flags
+        if (nz == 0) fb_activate(a, tile, stamp, (int)(cur ^ 1u), false);   // revisit once more, only to retire the FRESH flags
         if (nz == 1 || nz == 2) {                              // no 3-D corner directions in dirs_
           const int mnx = bb & 7, mxx = (bb >> 3) & 7, mny = (bb >> 6) & 7, mxy = (bb >> 9) & 7, mnz = (bb >> 12) & 7, mxz = (bb >> 15) & 7;
           bool need = true;
@@ -258,6 +317,10 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
       }
     }
     grid.sync();
+    if (a.dbg && blockIdx.x == 0 && tid == 0 && gen < 256u) {
+      unsigned long long t_c; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_c));
+      a.dbg[4 * gen] = nwork; a.dbg[4 * gen + 1] = nchg; a.dbg[4 * gen + 2] = t_b - t_a; a.dbg[4 * gen + 3] = t_c - t_b;
+    }
     cur ^= 1u;
     ++gen;
   }

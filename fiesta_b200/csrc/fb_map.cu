@@ -36,14 +36,15 @@ struct fiesta_map {
   double *occ;
   unsigned long long *cnt;
   // tiles
-  uint32_t *tile_flag, *list[2], *changed[2], *changed_bbox[2];
+  uint32_t *tile_flag, *nb_flag, *list[2], *changed[2], *changed_bbox[2];
   CUtensorMap tmap;
   int wf_blocks, rr_blocks;
   // queues
-  uint32_t *touched;
+  uint32_t *touch_flag, *touch_list;
+  unsigned touch_epoch;
   uint32_t *ins, *del;
   size_t cap_ins, cap_del;
-  unsigned n_touched, n_ins, n_del;      // host view (valid after the last sync)
+  unsigned n_touch_tiles, n_ins, n_del;  // host view (valid after the last sync)
   FbCounters *d_ctr, *h_ctr;
   // per-call SetOccupancy staging
   uint32_t *h_ev, *d_ev;
@@ -56,6 +57,7 @@ struct fiesta_map {
   // queries
   double *d_qin, *d_qout; size_t cap_q;
   cudaEvent_t ev[4];
+  unsigned long long *d_dbg;
   fiesta_stats st;
 };
 
@@ -67,65 +69,76 @@ __global__ void k_reset_ray_ctr(FbCounters *c) {
 }
 __global__ void k_reset_esdf_ctr(FbCounters *c) {
   c->n_changed[0] = c->n_changed[1] = 0;
+  c->next_work[0] = c->next_work[1] = c->next_work[2] = c->next_work[3] = 0;
   c->generations = 0;
   c->voxels_changed = c->voxels_reset = c->tile_visits = 0;
 }
+__global__ void k_reset_touched(FbCounters *c) { c->n_touched = 0; }
 __global__ void k_reset_queues(FbCounters *c, int touched, int insdel) {
-  if (touched) c->n_touched = 0;
+  if (touched) c->n_touch_tiles = 0;
   if (insdel) c->n_ins = c->n_del = 0;
 }
 
 // O1 counter part for per-call SetOccupancy events staged on the host (ESDFMap.cpp:424-435).
-__global__ void k_apply_events(const uint32_t *ev, size_t n, unsigned long long *cnt, uint32_t *touched, FbCounters *ctr) {
+__global__ void k_apply_events(FbGeom g, const uint32_t *ev, size_t n, FbTouch t) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool first = false;
-  uint32_t ii = 0;
-  if (i < n) {
-    const uint32_t e = ev[i];
-    ii = e & 0x7fffffffu;
-    const unsigned long long old = atomicAdd(&cnt[ii], ((unsigned long long)(e >> 31) << 32) | 1ull);
-    first = (unsigned)(old & 0xffffffffull) == 0u;
-  }
-  const unsigned slot = fb_warp_append(&ctr->n_touched, first);
-  if (first) touched[slot] = ii;
+  if (i >= n) return;
+  const uint32_t e = ev[i];
+  fb_touch(g, t, e & 0x7fffffffu, e >> 31);
 }
 
-// O2: ESDFMap::UpdateOccupancy (ESDFMap.cpp:235-271), one thread per queued voxel.  Voxels are independent, so the
-// queue order does not matter for the result.
-__global__ void k_integrate(FbGeom g, const uint32_t *touched, unsigned n, unsigned long long *cnt, double *occ, uint32_t *cobs,
-                            uint32_t *occbits, uint32_t *ins, uint32_t *del, FbCounters *ctr, int global_map, double l_hit,
-                            double l_miss, double l_min, double l_max, double l_occ) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool push_ins = false, push_del = false;
-  uint32_t ii = 0;
-  if (i < n) {
-    ii = touched[i];
-    const unsigned long long c = cnt[ii];
-    const long long hit = (long long)(c >> 32), tot = (long long)(c & 0xffffffffull);
-    cnt[ii] = 0ull;                                                       // num_hit_ = num_miss_ = 0
-    const double upd = (hit >= tot - hit) ? l_hit : l_miss;               // majority vote, ties -> hit (:243)
-    if (cobs[ii] == FB_UNKNOWN) cobs[ii] = FB_INF;                        // first observation: distance_ = +infinity_ (:246-249)
-    double o = occ[ii];
-    const bool was = o > l_occ;                                           // Exist(idx) before (:242)
-    bool skip = (upd >= 0 && o >= l_max) || (upd <= 0 && o <= l_min);     // already clamped in that direction (:250-255)
-    if (!skip) {
-      if (!global_map) {                                                  // local map: forget voxels outside the previous box (:256-259)
-        const int z = ii % g.pz, y = (ii / g.pz) % g.gy, x = ii / (g.pz * g.gy);
-        if (!fb_in_last_range(g, x, y, z)) { o = 0; cobs[ii] = FB_INF; }
+// O2: ESDFMap::UpdateOccupancy (ESDFMap.cpp:235-271).  One 128-thread CTA streams the counters of one queued 8^3 tile
+// (4 voxels = one 32-byte sector per thread); every voxel with pending observations is integrated exactly as the
+// reference does.  Voxels are independent, so the queue order does not matter for the result.
+__global__ void __launch_bounds__(128) k_integrate(FbGeom g, const uint32_t *tiles, unsigned ntiles, unsigned long long *cnt, double *occ,
+                                                   uint32_t *cobs, uint32_t *occbits, uint32_t *ins, uint32_t *del, FbCounters *ctr,
+                                                   int global_map, double l_hit, double l_miss, double l_min, double l_max, double l_occ) {
+  const int row = threadIdx.x >> 1, half = threadIdx.x & 1;
+  const int lx = row >> 3, ly = row & 7;
+  unsigned touched = 0;
+  for (unsigned w = blockIdx.x; w < ntiles; w += gridDim.x) {
+    const unsigned tile = tiles[w];
+    const int tz = tile % g.tz, ty = (tile / g.tz) % g.ty, tx = tile / (g.tz * g.ty);
+    const int x = tx * 8 + lx, y = ty * 8 + ly, z0 = tz * 8 + half * 4;
+    unsigned long long c[4] = {0, 0, 0, 0};
+    const bool inside = x < g.gx && y < g.gy && z0 < g.pz;             // pz is a multiple of 4: the 4 voxels are in the array
+    const long long base = fb_ii(g, x, y, z0);
+    if (inside) {
+      const ulonglong2 a = reinterpret_cast<const ulonglong2 *>(cnt + base)[0], b = reinterpret_cast<const ulonglong2 *>(cnt + base)[1];
+      c[0] = a.x; c[1] = a.y; c[2] = b.x; c[3] = b.y;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      bool push_ins = false, push_del = false;
+      const uint32_t ii = (uint32_t)(base + k);
+      if (c[k] != 0ull) {
+        ++touched;
+        const long long hit = (long long)(c[k] >> 32), tot = (long long)(c[k] & 0xffffffffull);
+        cnt[ii] = 0ull;                                                     // num_hit_ = num_miss_ = 0
+        const double upd = (hit >= tot - hit) ? l_hit : l_miss;             // majority vote, ties -> hit (:243)
+        if (cobs[ii] == FB_UNKNOWN) cobs[ii] = FB_INF;                      // first observation: distance_ = +infinity_ (:246-249)
+        double o = occ[ii];
+        const bool was = o > l_occ;                                         // Exist(idx) before (:242)
+        const bool skip = (upd >= 0 && o >= l_max) || (upd <= 0 && o <= l_min);   // already clamped in that direction (:250-255)
+        if (!skip) {
+          if (!global_map && !fb_in_last_range(g, x, y, z0 + k)) { o = 0; cobs[ii] = FB_INF; }   // local map (:256-259)
+          double s = o + upd;
+          s = s > l_min ? s : l_min;
+          s = s < l_max ? s : l_max;
+          occ[ii] = s;
+          const bool now = s > l_occ;
+          if (now && !was) { push_ins = true; atomicOr(&occbits[ii >> 5], 1u << (ii & 31)); }          // insert_queue_.push (:263-264)
+          else if (!now && was) { push_del = true; atomicAnd(&occbits[ii >> 5], ~(1u << (ii & 31))); }  // delete_queue_.push (:265-266)
+        }
       }
-      double s = o + upd;
-      s = s > l_min ? s : l_min;
-      s = s < l_max ? s : l_max;
-      occ[ii] = s;
-      const bool now = s > l_occ;
-      if (now && !was) { push_ins = true; atomicOr(&occbits[ii >> 5], 1u << (ii & 31)); }        // insert_queue_.push (:263-264)
-      else if (!now && was) { push_del = true; atomicAnd(&occbits[ii >> 5], ~(1u << (ii & 31))); } // delete_queue_.push (:265-266)
+      const unsigned si = fb_warp_append(&ctr->n_ins, push_ins);
+      if (push_ins) ins[si] = ii;
+      const unsigned sd = fb_warp_append(&ctr->n_del, push_del);
+      if (push_del) del[sd] = ii;
     }
   }
-  const unsigned si = fb_warp_append(&ctr->n_ins, push_ins);
-  if (push_ins) ins[si] = ii;
-  const unsigned sd = fb_warp_append(&ctr->n_del, push_del);
-  if (push_del) del[sd] = ii;
+  touched = __reduce_add_sync(0xffffffffu, touched);
+  if ((threadIdx.x & 31) == 0 && touched) atomicAdd(&ctr->n_touched, touched);
 }
 
 // distance_buffer_ value of a record (ESDFMap.cpp:122-123, 198, 247): exact because the stored obstacle coordinate is exact.
@@ -245,13 +258,14 @@ static int ensure(T **ptr, size_t *cap, size_t need, bool keep, cudaStream_t s) 
 static int fetch_counters(fiesta_map *m) {
   CK(cudaMemcpyAsync(m->h_ctr, m->d_ctr, sizeof(FbCounters), cudaMemcpyDeviceToHost, m->stream));
   CK(cudaStreamSynchronize(m->stream));
-  m->n_touched = m->h_ctr->n_touched; m->n_ins = m->h_ctr->n_ins; m->n_del = m->h_ctr->n_del;
+  m->n_touch_tiles = m->h_ctr->n_touch_tiles; m->n_ins = m->h_ctr->n_ins; m->n_del = m->h_ctr->n_del;
   return FIESTA_OK;
 }
 static int flush_events(fiesta_map *m) {
   if (m->n_ev == 0) return FIESTA_OK;
   CK(cudaMemcpyAsync(m->d_ev, m->h_ev, m->n_ev * sizeof(uint32_t), cudaMemcpyHostToDevice, m->stream));
-  k_apply_events<<<(unsigned)((m->n_ev + 255) / 256), 256, 0, m->stream>>>(m->d_ev, m->n_ev, m->cnt, m->touched, m->d_ctr);
+  FbTouch t = {m->cnt, m->touch_flag, m->touch_list, m->touch_epoch, m->d_ctr};
+  k_apply_events<<<(unsigned)((m->n_ev + 255) / 256), 256, 0, m->stream>>>(m->g, m->d_ev, m->n_ev, t);
   m->st.kernel_launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(m->stream));                                   // the pinned buffer is reused immediately
@@ -282,8 +296,8 @@ void fiesta_destroy(fiesta_map *m) {
   if (!m) return;
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
-  void *dev[] = {m->cobs, m->cobs_b, m->stamp[0], m->stamp[1], m->occbits, m->occ, m->cnt, m->tile_flag, m->list[0], m->list[1],
-                 m->changed[0], m->changed[1], m->changed_bbox[0], m->changed_bbox[1], m->touched, m->ins, m->del, m->d_ctr, m->d_ev,
+  void *dev[] = {m->cobs, m->cobs_b, m->stamp[0], m->stamp[1], m->occbits, m->occ, m->cnt, m->tile_flag, m->nb_flag, m->list[0], m->list[1],
+                 m->changed[0], m->changed[1], m->changed_bbox[0], m->changed_bbox[1], m->touch_flag, m->touch_list, m->ins, m->del, m->d_ctr, m->d_ev,
                  m->d_xyz, m->ray_list, m->ray_len, m->ray_reach, m->ray_act, m->ray_dirty, m->d_qin, m->d_qout};
   for (void *p : dev) if (p) cudaFree(p);
   if (m->h_ctr) cudaFreeHost(m->h_ctr);
@@ -347,8 +361,8 @@ int fiesta_create(const fiesta_config *cfg, fiesta_map **out) {
   CKD(cudaMalloc((void **)&m->stamp[0], P * 4)); CKD(cudaMalloc((void **)&m->stamp[1], P * 4));
   CKD(cudaMalloc((void **)&m->occbits, nbits * 4));
   CKD(cudaMalloc((void **)&m->occ, P * 8)); CKD(cudaMalloc((void **)&m->cnt, P * 8));
-  CKD(cudaMalloc((void **)&m->touched, P * 4));
-  CKD(cudaMalloc((void **)&m->tile_flag, (size_t)g.ntiles * 4));
+  CKD(cudaMalloc((void **)&m->touch_flag, (size_t)g.ntiles * 4)); CKD(cudaMalloc((void **)&m->touch_list, (size_t)g.ntiles * 4));
+  CKD(cudaMalloc((void **)&m->tile_flag, (size_t)g.ntiles * 4)); CKD(cudaMalloc((void **)&m->nb_flag, (size_t)g.ntiles * 4));
   for (int k = 0; k < 2; ++k) {
     CKD(cudaMalloc((void **)&m->list[k], (size_t)g.ntiles * 4));
     CKD(cudaMalloc((void **)&m->changed[k], (size_t)g.ntiles * 4));
@@ -362,7 +376,9 @@ int fiesta_create(const fiesta_config *cfg, fiesta_map **out) {
   CKD(cudaMemsetAsync(m->stamp[0], 0, P * 4, m->stream)); CKD(cudaMemsetAsync(m->stamp[1], 0, P * 4, m->stream));
   CKD(cudaMemsetAsync(m->occbits, 0, nbits * 4, m->stream));
   CKD(cudaMemsetAsync(m->occ, 0, P * 8, m->stream)); CKD(cudaMemsetAsync(m->cnt, 0, P * 8, m->stream));
-  CKD(cudaMemsetAsync(m->tile_flag, 0, (size_t)g.ntiles * 4, m->stream));
+  CKD(cudaMemsetAsync(m->tile_flag, 0, (size_t)g.ntiles * 4, m->stream)); CKD(cudaMemsetAsync(m->nb_flag, 0, (size_t)g.ntiles * 4, m->stream));
+  CKD(cudaMemsetAsync(m->touch_flag, 0, (size_t)g.ntiles * 4, m->stream));
+  m->touch_epoch = 1;
   memset(m->h_ctr, 0, sizeof(FbCounters));
   m->h_ctr->gen_stamp = 1;
   CKD(cudaMemcpyAsync(m->d_ctr, m->h_ctr, sizeof(FbCounters), cudaMemcpyHostToDevice, m->stream));
@@ -494,7 +510,7 @@ int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, co
   }
   if ((r = ensure(&m->ray_list, &m->cap_ray_list, (size_t)a.cap * (size_t)n, false, m->stream))) return r;
   a.cnt = m->cnt; a.stamp[0] = m->stamp[0]; a.stamp[1] = m->stamp[1];
-  a.touched = m->touched; a.touched_cap = (unsigned)(g.ptotal > 0xffffffffLL ? 0xffffffffu : (unsigned)g.ptotal);
+  a.touch_flag = m->touch_flag; a.touch_list = m->touch_list; a.touch_epoch = m->touch_epoch;
   a.ray_list = m->ray_list; a.ray_len = m->ray_len; a.ray_reach = m->ray_reach; a.ray_act = m->ray_act; a.ray_dirty = m->ray_dirty; a.ctr = m->d_ctr;
   CK(cudaEventRecord(m->ev[0], m->stream));
   k_reset_ray_ctr<<<1, 1, 0, m->stream>>>(m->d_ctr);
@@ -506,7 +522,7 @@ int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, co
   CK(cudaEventElapsedTime(&m->st.ms_raycast, m->ev[0], m->ev[1]));
   m->st.rays_cast = m->h_ctr->rays_cast; m->st.rays_dropped = m->h_ctr->rays_dropped;
   m->st.ray_voxels = (int64_t)m->h_ctr->ray_voxels; m->st.raycast_rounds = m->h_ctr->ray_rounds;
-  m->st.touched_voxels = m->n_touched;
+  m->st.touched_voxels = (int64_t)m->n_touch_tiles * 512;
   if (m->h_ctr->ray_error == 3) { set_error("fiesta_raycast_frame: stamp resolution did not converge"); return FIESTA_ERR_LIMIT; }
   return FIESTA_OK;
 }
@@ -522,7 +538,7 @@ int fiesta_raycast_frame(fiesta_map *m, const float *xyz, int64_t n, const doubl
 
 int fiesta_check_update(fiesta_map *m) {
   if (!m) return 0;
-  return (m->n_ev > 0 || m->n_touched > 0) ? 1 : 0;                       // !occupancy_queue_.empty(), ESDFMap.cpp:229
+  return (m->n_ev > 0 || m->n_touch_tiles > 0) ? 1 : 0;                       // !occupancy_queue_.empty(), ESDFMap.cpp:229
 }
 
 int fiesta_update_occupancy(fiesta_map *m, int global_map) {
@@ -533,21 +549,25 @@ int fiesta_update_occupancy(fiesta_map *m, int global_map) {
   cudaEventRecord(m->ev[0], m->stream);
   if ((r = flush_events(m))) return -r;
   if ((r = fetch_counters(m))) return -r;
-  const unsigned n = m->n_touched;
-  m->st.occupancy_updates = n;
+  const unsigned n = m->n_touch_tiles;
+  m->st.occupancy_updates = 0;
   if (n) {
-    if ((r = ensure(&m->ins, &m->cap_ins, (size_t)m->n_ins + n, true, m->stream))) return -r;
-    if ((r = ensure(&m->del, &m->cap_del, (size_t)m->n_del + n, true, m->stream))) return -r;
-    k_integrate<<<(n + 255) / 256, 256, 0, m->stream>>>(m->g, m->touched, n, m->cnt, m->occ, m->cobs, m->occbits, m->ins, m->del, m->d_ctr,
-                                                       global_map, m->l_hit, m->l_miss, m->l_min, m->l_max, m->l_occ);
+    if ((r = ensure(&m->ins, &m->cap_ins, (size_t)m->n_ins + (size_t)n * 512, true, m->stream))) return -r;
+    if ((r = ensure(&m->del, &m->cap_del, (size_t)m->n_del + (size_t)n * 512, true, m->stream))) return -r;
+    k_reset_touched<<<1, 1, 0, m->stream>>>(m->d_ctr);
+    const unsigned blocks = n < 148u * 16u ? n : 148u * 16u;
+    k_integrate<<<blocks, 128, 0, m->stream>>>(m->g, m->touch_list, n, m->cnt, m->occ, m->cobs, m->occbits, m->ins, m->del, m->d_ctr,
+                                              global_map, m->l_hit, m->l_miss, m->l_min, m->l_max, m->l_occ);
     k_reset_queues<<<1, 1, 0, m->stream>>>(m->d_ctr, 1, 0);
-    m->st.kernel_launches += 2;
+    m->touch_epoch++;
+    m->st.kernel_launches += 3;
     if (cudaGetLastError() != cudaSuccess) { set_error("k_integrate launch failed"); return -FIESTA_ERR_CUDA; }
   }
   cudaEventRecord(m->ev[1], m->stream);
   if ((r = fetch_counters(m))) return -r;
   cudaEventElapsedTime(&m->st.ms_update_occupancy, m->ev[0], m->ev[1]);
-  m->st.touched_voxels = m->n_touched;
+  if (n) m->st.occupancy_updates = m->h_ctr->n_touched;
+  m->st.touched_voxels = 0;
   return (m->n_ins > 0 || m->n_del > 0) ? 1 : 0;                          // :270
 }
 
@@ -559,9 +579,12 @@ int fiesta_update_esdf(fiesta_map *m) {
   m->st.ms_update_esdf = m->st.ms_esdf_delete_scan = m->st.ms_esdf_wavefront = 0;
   if (m->n_ins == 0 && m->n_del == 0) return FIESTA_OK;
   FbEsdfArgs a;
-  a.cobs = m->cobs; a.cobs_b = m->cobs_b; a.occ = m->occ; a.occbits = m->occbits; a.tile_flag = m->tile_flag;
+  a.cobs = m->cobs; a.cobs_b = m->cobs_b; a.occ = m->occ; a.occbits = m->occbits; a.tile_flag = m->tile_flag; a.nb_flag = m->nb_flag;
   for (int k = 0; k < 2; ++k) { a.list[k] = m->list[k]; a.changed[k] = m->changed[k]; a.changed_bbox[k] = m->changed_bbox[k]; }
   a.ctr = m->d_ctr; a.l_occ = m->l_occ;
+  a.dbg = nullptr;
+  static const bool dbg_wf = getenv("FIESTA_DEBUG_WF") != nullptr;
+  if (dbg_wf) { if (!m->d_dbg) CK(cudaMalloc((void **)&m->d_dbg, 1024 * 8)); CK(cudaMemsetAsync(m->d_dbg, 0, 1024 * 8, m->stream)); a.dbg = m->d_dbg; }
   CK(cudaEventRecord(m->ev[0], m->stream));
   k_reset_esdf_ctr<<<1, 1, 0, m->stream>>>(m->d_ctr);
   m->st.kernel_launches++;
@@ -581,6 +604,13 @@ int fiesta_update_esdf(fiesta_map *m) {
   CK(cudaEventElapsedTime(&m->st.ms_esdf_wavefront, m->ev[2], m->ev[3]));
   m->st.voxels_changed = (int64_t)m->h_ctr->voxels_changed; m->st.voxels_reset = (int64_t)m->h_ctr->voxels_reset;
   m->st.tile_visits = (int64_t)m->h_ctr->tile_visits; m->st.generations = m->h_ctr->generations;
+  if (a.dbg) {
+    unsigned long long h[1024];
+    CK(cudaMemcpy(h, m->d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[wf] gens=%u", m->h_ctr->generations);
+    for (unsigned gI = 0; gI < m->h_ctr->generations && gI < 256; ++gI) fprintf(stderr, " | %llu/%llu %.0f+%.0fus", h[4 * gI], h[4 * gI + 1], h[4 * gI + 2] * 1e-3, h[4 * gI + 3] * 1e-3);
+    fprintf(stderr, "\n");
+  }
   return FIESTA_OK;
 }
 

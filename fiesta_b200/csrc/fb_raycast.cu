@@ -79,11 +79,9 @@ __device__ __forceinline__ int fb_endpoint(const FbRayArgs &a, long long i, doub
   return 1;
 }
 
-__device__ __forceinline__ void fb_count(const FbRayArgs &a, long long ii, unsigned occ) {
-  const unsigned long long old = atomicAdd(&a.cnt[ii], ((unsigned long long)occ << 32) | 1ull);
-  const bool first = (unsigned)(old & 0xffffffffull) == 0u;   // num_miss_ == 1 -> occupancy_queue_.push (ESDFMap.cpp:426-435)
-  const unsigned slot = fb_warp_append(&a.ctr->n_touched, first);
-  if (first && slot < a.touched_cap) a.touched[slot] = (uint32_t)ii;
+__device__ __forceinline__ void fb_count(const FbGeom &g, const FbRayArgs &a, long long ii, unsigned occ) {
+  FbTouch t = {a.cnt, a.touch_flag, a.touch_list, a.touch_epoch, a.ctr};
+  fb_touch(g, t, (unsigned)ii, occ);
 }
 
 // ---------------------------------------------------------------- endpoints
@@ -99,7 +97,7 @@ __global__ void k_ray_endpoints(FbGeom g, FbRayArgs a) {
     if (fb_pos_to_vox(g, px, py, pz, vx, vy, vz)) {
       long long ii; bool in_range;
       if (fb_resolve_vox(g, vx, vy, vz, ii, in_range)) {
-        if (in_range) fb_count(a, ii, kind == 1 ? 1u : 0u);
+        if (in_range) fb_count(g, a, ii, kind == 1 ? 1u : 0u);
         // set_occ_ ownership: lowest point index wins (Fiesta.h:227-230)
         atomicMax(&a.stamp[1][ii], (a.owner_tag << FB_RAY_BITS) | (FB_RAY_MASK - (unsigned)i));
       }
@@ -336,18 +334,7 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_ray_resolve(FbGeom g, FbRayAr
       const int t = t0 + (int)lane;
       bool cnt = false; unsigned ii = 0;
       if (t < R) { const unsigned e = __ldcg(&row[L - 1 - t]); cnt = (e >> 30) == FB_CLS_COUNT; ii = e & FB_LIST_IDX_MASK; }
-      bool first = false;
-      if (cnt) {
-        const unsigned long long old = atomicAdd(&a.cnt[ii], 1ull);
-        first = (unsigned)(old & 0xffffffffull) == 0u;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, first);
-      if (m) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&a.ctr->n_touched, (unsigned)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (first) a.touched[base + __popc(m & ((1u << lane) - 1u))] = ii;
-      }
+      if (cnt) fb_count(g, a, ii, 0u);
     }
   }
 }
