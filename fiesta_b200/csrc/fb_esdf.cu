@@ -116,32 +116,38 @@ __device__ __forceinline__ void tma_load_box(void *dst, const CUtensorMap *tmap,
       : "memory");
 }
 
-#define WF_THREADS 512
+#define WF_THREADS 256     // 2 voxels per thread (x and x+4): four CTAs = four independent tile pipelines per SM
 
-__global__ void __launch_bounds__(WF_THREADS, 2)
+__global__ void __launch_bounds__(WF_THREADS, 4)
 k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
-  __shared__ __align__(128) uint32_t buf[2][FB_BOX_WORDS];
-  __shared__ __align__(8) uint64_t mbar;
+  // buf[0], buf[1]: TMA landing buffers (tile k in buf[k&1], tile k+1 prefetched into the other); buf[2]: relaxation partner
+  __shared__ __align__(128) uint32_t buf[3][FB_BOX_WORDS];
+  __shared__ __align__(8) uint64_t mbar[2];
   __shared__ int s_bbox[6];
-  __shared__ unsigned s_w;
+  __shared__ unsigned s_next[3];            // {work index, tile id, 1 = needs a full visit} of the prefetched item
   // per z-row bit masks of the FRESH flags (bit = box z index), one set per relaxation buffer: lets a voxel find out with
   // 13 loads whether anything within reach is in the queue before it pays for the 24-neighbour evaluation
   __shared__ uint32_t fmask[2][FB_BOX * FB_BOX];
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
-  const int lx = tid >> 6, ly = (tid >> 3) & 7, lz = tid & 7;
-  const int s = (lx + FB_HALO) * (FB_BOX * FB_BOXZ) + (ly + FB_HALO) * FB_BOXZ + (lz + FB_ZPAD);
+  const int ly = (tid >> 3) & 7, lz = tid & 7;
+  int lxh[2], sh[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    lxh[h] = (tid >> 6) + 4 * h;
+    sh[h] = (lxh[h] + FB_HALO) * (FB_BOX * FB_BOXZ) + (ly + FB_HALO) * FB_BOXZ + (lz + FB_ZPAD);
+  }
   // parameters.h:55-68 again, as compile-time immediates for the unrolled relaxation loop
   constexpr int kd[24][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
                              {-1, -1, 0}, {1, 1, 0}, {0, -1, -1}, {0, 1, 1}, {-1, 0, -1}, {1, 0, 1},
                              {-1, 1, 0}, {1, -1, 0}, {0, -1, 1}, {0, 1, -1}, {1, 0, -1}, {-1, 0, 1},
                              {-2, 0, 0}, {2, 0, 0}, {0, -2, 0}, {0, 2, 0}, {0, 0, -2}, {0, 0, 2}};
 
-  if (tid == 0) mbar_init(&mbar, 1);
+  if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
   __syncthreads();
-  unsigned parity = 0;
+  unsigned parity[2] = {0u, 0u};
   unsigned cur = 0, gen = 0;
-  unsigned long long my_changed = 0, my_visits = 0;
+  unsigned long long my_visits = 0;
   const unsigned stamp0 = a.ctr->gen_stamp;   // stamp of generation 0 (seeded by k_seed_inserts / k_delete_scan)
 
   for (;;) {
@@ -150,133 +156,181 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
     unsigned long long t_a = 0;
     if (a.dbg && blockIdx.x == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
     const unsigned par = gen & 1u;
-    if (blockIdx.x == 0 && tid == 0) a.ctr->n_changed[par ^ 1u] = 0;   // last read two barriers ago
-
-    // ---------------- phase 1: relax every active tile against the previous generation (tiles fetched dynamically)
-    if (blockIdx.x == 0 && tid == 0) { a.ctr->next_work[par ^ 1u] = 0; a.ctr->next_work[2u + (par ^ 1u)] = 0; }
+    if (blockIdx.x == 0 && tid == 0) {                        // counters of the other parity were last read two barriers ago
+      a.ctr->n_changed[par ^ 1u] = 0; a.ctr->next_work[par ^ 1u] = 0; a.ctr->next_work[2u + (par ^ 1u)] = 0;
+    }
     const unsigned stamp_cur = stamp0 + gen;
+
+    // Fetch the next work item (dynamic distribution) and, if it needs a full visit, start its TMA load into buf[slot].
+    auto fetch = [&](int slot) {
+      const unsigned w = atomicAdd(&a.ctr->next_work[par], 1u);
+      unsigned tile = 0, full = 0;
+      if (w < nwork) {
+        tile = ld_cg_u32(&a.list[cur][w]);
+        full = ld_cg_u32(&a.nb_flag[tile]) == stamp_cur ? 1u : 0u;
+        if (full) {
+          const int tzc = tile % g.tz, tyc = (tile / g.tz) % g.ty, txc = tile / (g.tz * g.ty);
+          mbar_expect_tx(&mbar[slot], FB_BOX_WORDS * 4);
+          tma_load_box(buf[slot], &tmap, tzc * FB_TILE - FB_ZPAD, tyc * FB_TILE - FB_HALO, txc * FB_TILE - FB_HALO, &mbar[slot]);
+        }
+      }
+      s_next[0] = w; s_next[1] = tile; s_next[2] = full;
+    };
+
+    // ---------------- phase 1: relax every active tile against the previous generation
+    int slot = 0;
+    if (tid == 0) fetch(0);
+    __syncthreads();
     for (;;) {
-      if (tid == 0) s_w = atomicAdd(&a.ctr->next_work[par], 1u);
-      __syncthreads();
-      const unsigned w = s_w;
+      const unsigned w = s_next[0], tile = s_next[1], full = s_next[2];
       __syncthreads();
       if (w >= nwork) break;
-      const unsigned tile = ld_cg_u32(&a.list[cur][w]);
+      if (tid == 0) {
+        fetch(slot ^ 1);                                      // prefetch: overlaps the next tile's load with this tile's relaxation
+        s_bbox[0] = s_bbox[2] = s_bbox[4] = 8; s_bbox[1] = s_bbox[3] = s_bbox[5] = -1;
+        ++my_visits;
+      }
       const int tzc = tile % g.tz, tyc = (tile / g.tz) % g.ty, txc = tile / (g.tz * g.ty);
       const int x0 = txc * FB_TILE, y0 = tyc * FB_TILE, z0 = tzc * FB_TILE;
-      if (ld_cg_u32(&a.nb_flag[tile]) != stamp_cur) {
+      const int vy = y0 + ly, vz = z0 + lz;
+      if (!full) {
         // Queued only by itself: nothing within reach changed since its local fixpoint, so its FRESH voxels would pull the
         // same values again.  Just retire the flags (through the staging grid, so that neighbours relaxing in this very
         // generation still see them).
-        const int vx = x0 + lx, vy = y0 + ly, vz = z0 + lz;
-        if (fb_in_grid(g, vx, vy, vz)) { const long long ii = fb_ii(g, vx, vy, vz); a.cobs_b[ii] = __ldcg(&a.cobs[ii]) & FB_CODE_MASK; }
-        if (tid == 0) {
-          ++my_visits;
-          const unsigned slot = atomicAdd(&a.ctr->n_changed[par], 1u);
-          a.changed[par][slot] = tile;
-          a.changed_bbox[par][slot] = 0u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int vx = x0 + lxh[h];
+          if (fb_in_grid(g, vx, vy, vz)) { const long long ii = fb_ii(g, vx, vy, vz); a.cobs_b[ii] = __ldcg(&a.cobs[ii]) & FB_CODE_MASK; }
         }
+        if (tid == 0) {
+          const unsigned sl = atomicAdd(&a.ctr->n_changed[par], 1u);
+          a.changed[par][sl] = tile;
+          a.changed_bbox[par][sl] = 0u;
+        }
+        __syncthreads();
+        slot ^= 1;                                            // the prefetched item (if any) landed in the other buffer
         continue;
       }
-      if (tid == 0) {
-        s_bbox[0] = s_bbox[2] = s_bbox[4] = 8; s_bbox[1] = s_bbox[3] = s_bbox[5] = -1;
-        mbar_expect_tx(&mbar, FB_BOX_WORDS * 4);
-        tma_load_box(buf[0], &tmap, z0 - FB_ZPAD, y0 - FB_HALO, x0 - FB_HALO, &mbar);
-      }
-      mbar_wait(&mbar, parity);
-      parity ^= 1u;
-      const int vx = x0 + lx, vy = y0 + ly, vz = z0 + lz;
-      const uint32_t orig = buf[0][s];
-      for (int k = tid; k < FB_BOX_WORDS; k += WF_THREADS) buf[1][k] = buf[0][k];   // halo must exist in both buffers
+      mbar_wait(&mbar[slot], parity[slot]);
+      parity[slot] ^= 1u;
+      uint32_t *L = buf[slot], *S = buf[2];
+      for (int k = tid; k < FB_BOX_WORDS; k += WF_THREADS) S[k] = L[k];   // the halo must exist in both relaxation buffers
       if (tid < FB_BOX * FB_BOX) {                            // FRESH mask of every z-row of the box (halo bits never change)
         uint32_t mk = 0;
 #pragma unroll
-        for (int z = 0; z < FB_BOXZ; ++z) mk |= (buf[0][tid * FB_BOXZ + z] >> 31) << z;
+        for (int z = 0; z < FB_BOXZ; ++z) mk |= (L[tid * FB_BOXZ + z] >> 31) << z;
         fmask[0][tid] = mk; fmask[1][tid] = mk;
       }
-      // A voxel relaxes iff it has been observed (unknown voxels are barriers: distance_ = -10000 is never > tmp,
-      // ESDFMap.cpp:382) and lies inside the update box (only in-box voxels are ever queued, ESDFMap.cpp:351,378).
-      const uint32_t ocode = orig & FB_CODE_MASK;
-      const bool updatable = ocode != FB_UNKNOWN && fb_in_range(g, vx, vy, vz);
-      unsigned nmask = 0xffffffu;
-      if (!g.box_is_full) {                                  // VoxInRange(new_pos), ESDFMap.cpp:351
-        nmask = 0;
+      uint32_t orig[2], mine[2], fresh[2], nmask[2];
+      bool updatable[2];
 #pragma unroll
-        for (int k = 0; k < 24; ++k)
-          if (fb_in_range(g, vx + kd[k][0], vy + kd[k][1], vz + kd[k][2])) nmask |= 1u << k;
+      for (int h = 0; h < 2; ++h) {
+        const int vx = x0 + lxh[h];
+        orig[h] = L[sh[h]];
+        mine[h] = orig[h] & FB_CODE_MASK;                     // code without the flag
+        fresh[h] = orig[h] >> 31;                             // changed in the previous generation (global flag)
+        // A voxel relaxes iff it has been observed (unknown voxels are barriers: distance_ = -10000 is never > tmp,
+        // ESDFMap.cpp:382) and lies inside the update box (only in-box voxels are ever queued, ESDFMap.cpp:351,378).
+        updatable[h] = mine[h] != FB_UNKNOWN && fb_in_range(g, vx, vy, vz);
+        nmask[h] = 0xffffffu;
+        if (!g.box_is_full) {                                 // VoxInRange(new_pos), ESDFMap.cpp:351
+          nmask[h] = 0;
+#pragma unroll
+          for (int k = 0; k < 24; ++k)
+            if (fb_in_range(g, vx + kd[k][0], vy + kd[k][1], vz + kd[k][2])) nmask[h] |= 1u << k;
+        }
       }
       __syncthreads();
-      uint32_t mine = ocode;                                 // code without the flag
-      uint32_t fresh = orig >> 31;                           // changed in the previous generation (global flag)
-      int cb = 0;
+      int cb = 0;                                             // 0: read L / write S, 1: read S / write L
       for (;;) {
-        uint32_t best = mine;
-        bool active = false;
-        if (updatable) {
-          const uint32_t *fm = fmask[cb];
-          const int r = (lx + FB_HALO) * FB_BOX + (ly + FB_HALO), zb = lz + FB_ZPAD;
-          uint32_t any5 = (fm[r] >> (zb - 2)) & 0x1fu;                                   // self, z+-1, z+-2
-          uint32_t any3 = ((fm[r - FB_BOX] | fm[r + FB_BOX] | fm[r - 1] | fm[r + 1]) >> (zb - 1)) & 7u;   // x+-1 / y+-1 rows: z-1..z+1
-          uint32_t any1 = ((fm[r - FB_BOX - 1] | fm[r - FB_BOX + 1] | fm[r + FB_BOX - 1] | fm[r + FB_BOX + 1] |
-                            fm[r - 2 * FB_BOX] | fm[r + 2 * FB_BOX] | fm[r - 2] | fm[r + 2]) >> zb) & 1u;   // planar diagonals and +-2 steps
-          active = (any5 | any3 | any1) != 0u;
-        }
-        if (active) {
-          unsigned bestd = 0xffffffffu;
-          if (mine >= 2u) { int ox, oy, oz; fb_unpack(mine, ox, oy, oz); ox -= vx; oy -= vy; oz -= vz; bestd = (unsigned)(ox * ox + oy * oy + oz * oz); }
-          const uint32_t *b = buf[cb];
+        const uint32_t *b = cb ? S : L;
+        uint32_t *o = cb ? L : S;
+        const uint32_t *fm = fmask[cb];
+        unsigned anyfresh = 0;
 #pragma unroll
-          for (int k = 0; k < 24; ++k) {
-            const uint32_t wn = b[s + kd[k][0] * (FB_BOX * FB_BOXZ) + kd[k][1] * FB_BOXZ + kd[k][2]];
-            const uint32_t c = wn & FB_CODE_MASK;
-            // candidate iff the neighbour has a closest obstacle (ESDFMap.cpp:353) and either it is in the queue (its
-            // push phase, :375-391) or this voxel is (its pull phase, :349-367)
-            if (c >= 2u && ((nmask >> k) & 1u) && ((wn >> 31) | fresh)) {
-              int ox, oy, oz; fb_unpack(c, ox, oy, oz); ox -= vx; oy -= vy; oz -= vz;
-              const unsigned d = (unsigned)(ox * ox + oy * oy + oz * oz);
-              if (d < bestd || (d == bestd && c < best)) { bestd = d; best = c; }   // strict improvement; ties -> smallest coordinate
+        for (int h = 0; h < 2; ++h) {
+          uint32_t best = mine[h];
+          bool active = false;
+          if (updatable[h]) {
+            const int r = (lxh[h] + FB_HALO) * FB_BOX + (ly + FB_HALO), zb = lz + FB_ZPAD;
+            const uint32_t any5 = (fm[r] >> (zb - 2)) & 0x1fu;                                   // self, z+-1, z+-2
+            const uint32_t any3 = ((fm[r - FB_BOX] | fm[r + FB_BOX] | fm[r - 1] | fm[r + 1]) >> (zb - 1)) & 7u;   // x+-1 / y+-1 rows
+            const uint32_t any1 = ((fm[r - FB_BOX - 1] | fm[r - FB_BOX + 1] | fm[r + FB_BOX - 1] | fm[r + FB_BOX + 1] |
+                                    fm[r - 2 * FB_BOX] | fm[r + 2 * FB_BOX] | fm[r - 2] | fm[r + 2]) >> zb) & 1u;   // diagonals, +-2 steps
+            active = (any5 | any3 | any1) != 0u;
+          }
+          if (active) {
+            const int vx = x0 + lxh[h];
+            unsigned bestd = 0xffffffffu;
+            if (best >= 2u) { int ox, oy, oz; fb_unpack(best, ox, oy, oz); ox -= vx; oy -= vy; oz -= vz; bestd = (unsigned)(ox * ox + oy * oy + oz * oz); }
+#pragma unroll
+            for (int k = 0; k < 24; ++k) {
+              const uint32_t wn = b[sh[h] + kd[k][0] * (FB_BOX * FB_BOXZ) + kd[k][1] * FB_BOXZ + kd[k][2]];
+              const uint32_t c = wn & FB_CODE_MASK;
+              // candidate iff the neighbour has a closest obstacle (ESDFMap.cpp:353) and either it is in the queue (its
+              // push phase, :375-391) or this voxel is (its pull phase, :349-367)
+              if (c >= 2u && ((nmask[h] >> k) & 1u) && ((wn >> 31) | fresh[h])) {
+                int ox, oy, oz; fb_unpack(c, ox, oy, oz); ox -= vx; oy -= vy; oz -= vz;
+                const unsigned d = (unsigned)(ox * ox + oy * oy + oz * oz);
+                if (d < bestd || (d == bestd && c < best)) { bestd = d; best = c; }   // strict improvement; ties -> smallest coordinate
+              }
             }
           }
-        }
-        fresh = best != mine ? 1u : 0u;
-        buf[cb ^ 1][s] = best | (fresh << 31);
-        {                                                     // a warp owns 4 interior z-rows: lanes 8r..8r+7 = row (lx, ly0 + r)
-          const uint32_t bal = __ballot_sync(0xffffffffu, fresh != 0u);
+          fresh[h] = best != mine[h] ? 1u : 0u;
+          mine[h] = best;
+          o[sh[h]] = best | (fresh[h] << 31);
+          // a warp owns 4 interior z-rows per h: lanes 8r..8r+7 = row (lx, ly0 + r)
+          const uint32_t bal = __ballot_sync(0xffffffffu, fresh[h] != 0u);
           const int lane = tid & 31;
           if (lane < 4) {
-            const int r = (lx + FB_HALO) * FB_BOX + (((tid >> 5) & 1) * 4 + lane + FB_HALO);
-            fmask[cb ^ 1][r] = (fmask[cb][r] & ~(0xffu << FB_ZPAD)) | (((bal >> (8 * lane)) & 0xffu) << FB_ZPAD);
+            const int r = (lxh[h] + FB_HALO) * FB_BOX + (((tid >> 5) & 1) * 4 + lane + FB_HALO);
+            fmask[cb ^ 1][r] = (fm[r] & ~(0xffu << FB_ZPAD)) | (((bal >> (8 * lane)) & 0xffu) << FB_ZPAD);
           }
+          anyfresh |= fresh[h];
         }
-        const int any = __syncthreads_or((int)fresh);
-        mine = best;
+        const int any = __syncthreads_or((int)anyfresh);
         cb ^= 1;
         if (!any) break;
       }
-      const bool changed = mine != ocode;                    // changed during this generation -> FRESH for the next one
-      const uint32_t outw = mine | (changed ? FB_FRESH : 0u);
-      if (changed) {
-        atomicMin(&s_bbox[0], lx); atomicMax(&s_bbox[1], lx);
-        atomicMin(&s_bbox[2], ly); atomicMax(&s_bbox[3], ly);
-        atomicMin(&s_bbox[4], lz); atomicMax(&s_bbox[5], lz);
+      int nch = 0;
+      bool diff = false;
+      uint32_t outw[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const bool changed = mine[h] != (orig[h] & FB_CODE_MASK);   // changed during this generation -> FRESH for the next one
+        outw[h] = mine[h] | (changed ? FB_FRESH : 0u);
+        if (changed) {
+          ++nch;
+          atomicMin(&s_bbox[0], lxh[h]); atomicMax(&s_bbox[1], lxh[h]);
+          atomicMin(&s_bbox[2], ly); atomicMax(&s_bbox[3], ly);
+          atomicMin(&s_bbox[4], lz); atomicMax(&s_bbox[5], lz);
+        }
+        diff = diff || outw[h] != orig[h];
       }
-      const int nchanged = __syncthreads_count(changed);
-      const int dirty = __syncthreads_or(outw != orig);      // also true when only stale FRESH flags must be cleared
-      if (dirty && fb_in_grid(g, vx, vy, vz)) a.cobs_b[fb_ii(g, vx, vy, vz)] = outw;   // stage the whole tile interior
-      if (tid == 0) {
-        ++my_visits;
-        if (dirty) {
-          my_changed += (unsigned long long)nchanged;
-          const unsigned slot = atomicAdd(&a.ctr->n_changed[par], 1u);
-          a.changed[par][slot] = tile;
-          a.changed_bbox[par][slot] = nchanged ? ((unsigned)s_bbox[0] | ((unsigned)s_bbox[1] << 3) | ((unsigned)s_bbox[2] << 6) |
-                                                  ((unsigned)s_bbox[3] << 9) | ((unsigned)s_bbox[4] << 12) | ((unsigned)s_bbox[5] << 15) | (1u << 18))
-                                               : 0u;
+      const int nchanged = __syncthreads_count(nch > 0) ;      // threads with a change (exact voxel count accumulated below)
+      const int dirty = __syncthreads_or(diff);               // also true when only stale FRESH flags must be retired
+      if (dirty) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int vx = x0 + lxh[h];
+          if (fb_in_grid(g, vx, vy, vz)) a.cobs_b[fb_ii(g, vx, vy, vz)] = outw[h];   // stage the whole tile interior
         }
       }
-      // generic-proxy writes to buf[] must be ordered before the next async-proxy (TMA) write into buf[0]
+      {
+        const unsigned c2 = __reduce_add_sync(0xffffffffu, (unsigned)nch);     // exact number of changed voxels, per warp
+        if ((tid & 31) == 0 && c2) atomicAdd(&a.ctr->voxels_changed, (unsigned long long)c2);
+      }
+      if (tid == 0 && dirty) {
+        const unsigned sl = atomicAdd(&a.ctr->n_changed[par], 1u);
+        a.changed[par][sl] = tile;
+        a.changed_bbox[par][sl] = nchanged ? ((unsigned)s_bbox[0] | ((unsigned)s_bbox[1] << 3) | ((unsigned)s_bbox[2] << 6) |
+                                              ((unsigned)s_bbox[3] << 9) | ((unsigned)s_bbox[4] << 12) | ((unsigned)s_bbox[5] << 15) | (1u << 18))
+                                           : 0u;
+      }
+      // generic-proxy accesses to buf[slot] must be ordered before the async-proxy (TMA) write of a later prefetch into it
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
+      slot ^= 1;
     }
     grid.sync();
 
@@ -287,18 +341,22 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
     const unsigned nchg = ld_cg_u32(&a.ctr->n_changed[par]);
     const unsigned stamp = stamp0 + gen + 1u;
     for (;;) {
-      if (tid == 0) s_w = atomicAdd(&a.ctr->next_work[2u + par], 1u);
+      if (tid == 0) s_next[0] = atomicAdd(&a.ctr->next_work[2u + par], 1u);
       __syncthreads();
-      const unsigned w = s_w;
+      const unsigned w = s_next[0];
       __syncthreads();
       if (w >= nchg) break;
       const unsigned tile = ld_cg_u32(&a.changed[par][w]);
       const unsigned bb = ld_cg_u32(&a.changed_bbox[par][w]);
       const int tzc = tile % g.tz, tyc = (tile / g.tz) % g.ty, txc = tile / (g.tz * g.ty);
-      const int vx = txc * FB_TILE + lx, vy = tyc * FB_TILE + ly, vz = tzc * FB_TILE + lz;
-      if (fb_in_grid(g, vx, vy, vz)) {
-        const long long ii = fb_ii(g, vx, vy, vz);
-        a.cobs[ii] = __ldcg(&a.cobs_b[ii]);
+      const int vy = tyc * FB_TILE + ly, vz = tzc * FB_TILE + lz;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int vx = txc * FB_TILE + lxh[h];
+        if (fb_in_grid(g, vx, vy, vz)) {
+          const long long ii = fb_ii(g, vx, vy, vz);
+          a.cobs[ii] = __ldcg(&a.cobs_b[ii]);
+        }
       }
       if (tid < 27 && (bb >> 18)) {                            // some record changed: its new value must reach the neighbours
         const int ox = tid / 9 - 1, oy = (tid / 3) % 3 - 1, oz = tid % 3 - 1;
@@ -325,7 +383,6 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
     ++gen;
   }
   if (tid == 0) {
-    if (my_changed) atomicAdd(&a.ctr->voxels_changed, my_changed);
     if (my_visits) atomicAdd(&a.ctr->tile_visits, my_visits);
     if (blockIdx.x == 0) { a.ctr->generations = gen; a.ctr->gen_stamp = stamp0 + gen + 1u; }
   }
