@@ -25,7 +25,7 @@ I3 = C.c_int * 3
 
 class Config(C.Structure):
     _fields_ = [("origin", C.c_double * 3), ("resolution", C.c_double), ("map_size", C.c_double * 3),
-                ("device", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("device", C.c_int32), ("mode", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 class RaycastParams(C.Structure):
@@ -34,10 +34,10 @@ class RaycastParams(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
-        "occupancy_updates", "inserts", "deletes", "voxels_changed", "voxels_reset", "tile_visits", "generations",
+        "occupancy_updates", "inserts", "deletes", "voxels_changed", "expansions", "voxels_reset", "tile_visits", "generations",
         "rays_cast", "rays_dropped", "ray_voxels", "raycast_rounds", "touched_voxels", "kernel_launches")] + [
         (n, C.c_float) for n in ("ms_raycast", "ms_update_occupancy", "ms_update_esdf", "ms_esdf_delete_scan",
-                                 "ms_esdf_wavefront")] + [("reserved_f", C.c_float * 3)]
+                                 "ms_esdf_wavefront")] + [("reserved_f", C.c_float * 1)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved_f"}
@@ -87,13 +87,15 @@ def _f64(a):
 class ESDFMap:
     """Mirror of fiesta::ESDFMap (ESDFMap.h:111-164); every method forwards 1:1 to the C ABI."""
 
-    def __init__(self, origin, resolution, map_size, device=0):
+    def __init__(self, origin, resolution, map_size, device=0, mode="fast"):
         self._L = load_library()
         cfg = Config()
         cfg.origin = D3(*origin)
         cfg.resolution = float(resolution)
         cfg.map_size = D3(*map_size)
         cfg.device = int(device)
+        cfg.mode = {"fast": 0, "exact": 1}[mode]
+        self.mode = mode
         h = C.c_void_p()
         rc = self._L.fiesta_create(C.byref(cfg), C.byref(h))
         if rc != 0:

@@ -64,6 +64,7 @@ struct FbGeom {
 struct FbCounters {
   unsigned n_touched, n_ins, n_del;   // n_touched: voxels integrated by the last UpdateOccupancy
   unsigned n_touch_tiles;      // tiles holding pending observations (the occupancy queue)
+  unsigned n_xtouched;         // exact mode: voxels holding pending observations
   unsigned n_list[2];          // active-tile work lists (ping-pong)
   unsigned n_changed[2];       // changed-tile lists by generation parity
   unsigned next_work[4];       // dynamic tile fetch counters: [phase1 even, phase1 odd, phase2 even, phase2 odd]
@@ -74,7 +75,6 @@ struct FbCounters {
   unsigned rays_cast, rays_dropped, ray_rounds, ray_error;
   unsigned long long ray_voxels;
   unsigned long long voxels_changed, voxels_reset, tile_visits;
-  unsigned pad[1];
 };
 
 __host__ __device__ __forceinline__ uint32_t fb_pack(int x, int y, int z) {
@@ -121,12 +121,21 @@ struct FbTouch {
   uint32_t *touch_flag, *touch_list;
   unsigned epoch;
   FbCounters *ctr;
+  unsigned long long *tkey;   // exact mode only (else nullptr): per-voxel serial time of the first pending observation
+  uint32_t *xtouched;         // exact mode only: voxels with pending observations
 };
 // One observation of voxel ii (ESDFMap.cpp:424-435): num_miss_++, num_hit_ += occ; the first one since the last
-// integration (num_miss_ == 1) queues the voxel -- here: marks its 8^3 tile.
-__device__ __forceinline__ void fb_touch(const FbGeom &g, const FbTouch &t, unsigned ii, unsigned occ) {
+// integration (num_miss_ == 1) queues the voxel -- fast mode: marks its 8^3 tile; exact mode: lists the voxel and keeps
+// the serial time `key` of its earliest observation (= its position in occupancy_queue_).
+__device__ __forceinline__ void fb_touch(const FbGeom &g, const FbTouch &t, unsigned ii, unsigned occ, unsigned long long key) {
   const unsigned long long old = atomicAdd(&t.cnt[ii], ((unsigned long long)occ << 32) | 1ull);
-  if ((unsigned)(old & 0xffffffffull) == 0u) {
+  const bool first = (unsigned)(old & 0xffffffffull) == 0u;
+  if (t.tkey) {
+    atomicMin(&t.tkey[ii], key);
+    if (first) t.xtouched[atomicAdd(&t.ctr->n_xtouched, 1u)] = ii;
+    return;
+  }
+  if (first) {
     const unsigned z = ii % (unsigned)g.pz, xy = ii / (unsigned)g.pz, y = xy % (unsigned)g.gy, x = xy / (unsigned)g.gy;
     const unsigned tile = ((x >> 3) * g.ty + (y >> 3)) * g.tz + (z >> 3);
     if (__ldcg(&t.touch_flag[tile]) != t.epoch && atomicExch(&t.touch_flag[tile], t.epoch) != t.epoch)
@@ -164,6 +173,9 @@ struct FbRayArgs {
   uint32_t *stamp[2];
   uint32_t *touch_flag, *touch_list;
   unsigned touch_epoch;
+  unsigned long long *tkey;   // exact mode (else nullptr)
+  uint32_t *xtouched;
+  unsigned long long key_base;
   uint32_t *ray_list;     // [n][cap] row-major, reversed (t = 0 is the voxel before the last emitted one)
   int *ray_len, *ray_reach;
   unsigned *ray_act;      // per-round work list: rays that have to walk again

@@ -1,0 +1,544 @@
+// fiesta_b200 -- ORDER-EXACT mode of UpdateOccupancy / UpdateESDF (FIESTA_MODE_EXACT).
+//
+// The reference result is a function of its sequential FIFO order (/root/reference/src/ESDFMap.cpp:273-398): seeds in
+// insert_queue_/delete_queue_ order, dependants of a deleted obstacle in LIFO list order (:301-334), neighbours in dirs_
+// order, strict improvement, and every queue element seeing the writes of all earlier elements.  This file reproduces
+// that order with data-parallel kernels (the CPU model of exactly this formulation is oracle/exact_model.c, which matches
+// the sequential reference voxel for voxel):
+//
+//  * Every FIFO generation is one list E of (voxel) entries in queue order.  Element i at direction k acts at the
+//    timestamp ts = 32*i + k (its pull acts at 32*i + 24).
+//  * A voxel's state "as seen at time T" is a pure function of the snapshot at generation start and of the behaviour
+//    (dead / pulled code / pushes code) of the <= 25 elements that can write it: the lexicographic minimum (distance,
+//    timestamp) over their offers with timestamp < T that beat the snapshot -- exactly what a sequence of strict `>` tests
+//    in timestamp order leaves behind (x_state()).
+//  * An element's behaviour depends only on states at its own pop time (k_x_eval).  Starting from "everybody pushes its
+//    snapshot code", the behaviours are re-evaluated until none changes; element i is right once all elements before it
+//    are, so the fixpoint is the sequential execution (2-3 rounds in practice).
+//  * The last accepted write to a voxel in a generation is the lexicographic minimum over ALL offers; those writes, in
+//    timestamp order, are the live entries of the next generation (k_x_commit + ordered compaction).  Non-final accepted
+//    writes only create entries the reference skips as stale (:345), so dropping them changes nothing.
+//  * The doubly linked dependant lists are replaced by a per-voxel link time LS (time of the last relink; every accepted
+//    write relinks at the list front, :24-42): dependants of deleted obstacles are found by a dense scan and ordered by
+//    (position of the obstacle in delete_queue_, link time descending) = the order of the reference's list walk; their
+//    re-seeding ("first valid neighbour in dirs_ order", :308-321, which sees earlier re-seeded dependants) is iterated to
+//    its fixpoint the same way.
+//  * occupancy_queue_ order = order of first observation: every observation carries its serial time (host event number,
+//    or point index and position along the ray); the per-voxel minimum orders the integration, so insert_queue_ /
+//    delete_queue_ come out in the reference's order.
+#include <cub/cub.cuh>
+#include <stdio.h>
+#include "fb_common.cuh"
+#include "fb_exact.h"
+
+#define XNONE 0xffffffffu
+#define X_DEAD 0ull
+#define X_PULL 1ull
+#define X_PUSH 2ull
+
+__constant__ int x_dirs[24][3] = {
+    {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
+    {-1, -1, 0}, {1, 1, 0}, {0, -1, -1}, {0, 1, 1}, {-1, 0, -1}, {1, 0, 1},
+    {-1, 1, 0}, {1, -1, 0}, {0, -1, 1}, {0, 1, -1}, {1, 0, -1}, {-1, 0, 1},
+    {-2, 0, 0}, {2, 0, 0}, {0, -2, 0}, {0, 2, 0}, {0, 0, -2}, {0, 0, 2}};
+
+__device__ __forceinline__ void x_coords(const FbGeom &g, uint32_t ii, int &x, int &y, int &z) {
+  z = ii % (unsigned)g.pz; const unsigned xy = ii / (unsigned)g.pz; y = xy % (unsigned)g.gy; x = xy / (unsigned)g.gy;
+}
+__device__ __forceinline__ unsigned x_d2(int x, int y, int z, uint32_t c) {
+  int ox, oy, oz; fb_unpack(c, ox, oy, oz); ox -= x; oy -= y; oz -= z;
+  return (unsigned)(ox * ox + oy * oy + oz * oz);
+}
+__device__ __forceinline__ unsigned x_dist_of(int x, int y, int z, uint32_t c) { return c < 2u ? 0xffffffffu : x_d2(x, y, z, c); }
+
+struct XState { unsigned d; uint32_t c; unsigned ts; };
+
+// State of voxel (x,y,z) as seen at time T (exclusive) given the behaviours B of this generation's elements.
+__device__ __forceinline__ XState x_state(const FbGeom &g, const uint32_t *cobs, const uint32_t *M, const unsigned long long *B,
+                                          int x, int y, int z, unsigned T) {
+  XState s;
+  const long long v = fb_ii(g, x, y, z);
+  s.c = cobs[v] & FB_CODE_MASK; s.d = x_dist_of(x, y, z, s.c); s.ts = XNONE;
+  const unsigned d0 = s.d;
+  if (s.c == FB_UNKNOWN) return s;                             // never observed: distance_ = -10000 is never > tmp (:382)
+  if (!fb_in_range(g, x, y, z)) return s;                     // pushes only go to voxels inside the update box (:378)
+#pragma unroll 4
+  for (int k = 0; k < 24; ++k) {
+    const int qx = x - x_dirs[k][0], qy = y - x_dirs[k][1], qz = z - x_dirs[k][2];
+    if (!fb_in_grid(g, qx, qy, qz)) continue;
+    const unsigned j = M[fb_ii(g, qx, qy, qz)];
+    if (j == XNONE) continue;
+    const unsigned long long b = B[j];
+    if ((b >> 32) != X_PUSH) continue;
+    const unsigned ts = j * 32u + (unsigned)k;
+    if (ts >= T) continue;
+    const uint32_t c = (uint32_t)b;
+    const unsigned d = x_d2(x, y, z, c);
+    if (d < d0 && (d < s.d || (d == s.d && ts < s.ts))) { s.d = d; s.c = c; s.ts = ts; }
+  }
+  const unsigned j = M[v];
+  if (j != XNONE) {
+    const unsigned long long b = B[j];
+    if ((b >> 32) == X_PULL) {
+      const unsigned ts = j * 32u + 24u;
+      if (ts < T) {
+        const uint32_t c = (uint32_t)b;
+        const unsigned d = x_d2(x, y, z, c);
+        if (d < d0 && (d < s.d || (d == s.d && ts < s.ts))) { s.d = d; s.c = c; s.ts = ts; }
+      }
+    }
+  }
+  return s;
+}
+
+// ------------------------------------------------------------------ occupancy (ordered)
+__global__ void k_x_gather_keys(const uint32_t *vox, unsigned n, const unsigned long long *tkey, unsigned long long *keys) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = tkey[vox[i]];
+}
+
+// ESDFMap::UpdateOccupancy (ESDFMap.cpp:235-271) over the queue in first-observation order; flags mark insert / delete pushes.
+__global__ void k_x_integrate(FbGeom g, const uint32_t *vox, unsigned n, unsigned long long *cnt, double *occ, uint32_t *cobs,
+                              uint32_t *occbits, unsigned long long *tkey, uint8_t *f_ins, uint8_t *f_del, int global_map, double l_hit,
+                              double l_miss, double l_min, double l_max, double l_occ) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t ii = vox[i];
+  uint8_t pi = 0, pd = 0;
+  const unsigned long long c = cnt[ii];
+  const long long hit = (long long)(c >> 32), tot = (long long)(c & 0xffffffffull);
+  cnt[ii] = 0ull;
+  tkey[ii] = ~0ull;
+  const double upd = (hit >= tot - hit) ? l_hit : l_miss;
+  if (cobs[ii] == FB_UNKNOWN) cobs[ii] = FB_INF;
+  double o = occ[ii];
+  const bool was = o > l_occ;
+  const bool skip = (upd >= 0 && o >= l_max) || (upd <= 0 && o <= l_min);
+  if (!skip) {
+    if (!global_map) { int x, y, z; x_coords(g, ii, x, y, z); if (!fb_in_last_range(g, x, y, z)) { o = 0; cobs[ii] = FB_INF; } }
+    double s = o + upd;
+    s = s > l_min ? s : l_min;
+    s = s < l_max ? s : l_max;
+    occ[ii] = s;
+    const bool now = s > l_occ;
+    if (now && !was) { pi = 1; atomicOr(&occbits[ii >> 5], 1u << (ii & 31)); }
+    else if (!now && was) { pd = 1; atomicAnd(&occbits[ii >> 5], ~(1u << (ii & 31))); }
+  }
+  f_ins[i] = pi; f_del[i] = pd;
+}
+
+// ------------------------------------------------------------------ E1: insert seeds
+__global__ void k_x_flag_exist(const uint32_t *list, unsigned n, const double *occ, double l_occ, uint8_t *flags, int want) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = ((occ[list[i]] > l_occ) ? 1 : 0) == want;
+}
+__global__ void k_x_apply_seed(FbGeom g, const uint32_t *E, unsigned n, uint32_t *cobs, uint32_t *M, unsigned long long *LS, unsigned long long t0) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t ii = E[i];
+  int x, y, z; x_coords(g, ii, x, y, z);
+  cobs[ii] = fb_pack(x, y, z);                                 // closest_obstacle_ = self, distance_ = 0 (:286-287)
+  LS[ii] = t0 + i;                                             // InsertIntoList(idx, idx) (:288)
+  M[ii] = i;
+}
+
+// ------------------------------------------------------------------ E2: delete
+__global__ void k_x_del_minpos(const uint32_t *del, unsigned n, const double *occ, double l_occ, uint32_t *scratch) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !(occ[del[i]] > l_occ)) atomicMin(&scratch[del[i]], i);   // `if (!Exist(idx))` (:297); first occurrence wins
+}
+__global__ void k_x_del_flag(const uint32_t *del, unsigned n, const double *occ, double l_occ, const uint32_t *scratch, uint8_t *flags) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = (!(occ[del[i]] > l_occ) && scratch[del[i]] == i) ? 1 : 0;
+}
+__global__ void k_x_del_rank(const uint32_t *sel, unsigned n, uint32_t *scratch) {   // sel = deleted obstacles in queue order
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) scratch[sel[i]] = i;
+}
+// Dependants = voxels whose closest obstacle is a deleted one (the reference walks head_[idx] -> next_, :301).
+__global__ void k_x_scan_deps(FbGeom g, const uint32_t *cobs, const uint32_t *rank, const unsigned long long *LS, unsigned long long *k1,
+                              unsigned long long *k2, uint32_t *dv, unsigned *ndep, unsigned cap) {
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < g.ptotal; v += (long long)gridDim.x * blockDim.x) {
+    const uint32_t c = cobs[v] & FB_CODE_MASK;
+    bool dep = false;
+    unsigned r = 0;
+    if (c >= 2u) {
+      int ox, oy, oz; fb_unpack(c, ox, oy, oz);
+      r = rank[fb_ii(g, ox, oy, oz)];
+      dep = r != XNONE;
+    }
+    const unsigned slot = fb_warp_append(ndep, dep);
+    if (dep && slot < cap) { k1[slot] = r; k2[slot] = ~LS[v]; dv[slot] = (uint32_t)v; }   // ~LS: most recently linked first
+  }
+}
+__global__ void k_x_iota(uint32_t *a, unsigned n) { const unsigned i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = i; }
+__global__ void k_x_gather64(const unsigned long long *src, const uint32_t *idx, unsigned n, unsigned long long *dst) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) dst[i] = src[idx[i]];
+}
+__global__ void k_x_gather32(const uint32_t *src, const uint32_t *idx, unsigned n, uint32_t *dst) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) dst[i] = src[idx[i]];
+}
+__global__ void k_x_set_ord(const uint32_t *deps, unsigned n, uint32_t *ord, uint32_t *nc) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { ord[deps[i]] = i; nc[i] = FB_INF; }
+}
+// One round of the re-seeding fixpoint: dependant i takes the closest obstacle of the FIRST neighbour in dirs_ order that
+// has a valid one (:308-321); dependants processed earlier expose their new value, later ones their (deleted) old one.
+__global__ void k_x_reseed(FbGeom g, const uint32_t *deps, unsigned n, const uint32_t *cobs, const uint32_t *ord, const uint32_t *occbits,
+                           const uint32_t *nc_in, uint32_t *nc_out, unsigned *changed) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int x, y, z; x_coords(g, deps[i], x, y, z);
+  uint32_t res = FB_INF;
+  for (int k = 0; k < 24; ++k) {
+    const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
+    if (!fb_in_range(g, nx, ny, nz) || !fb_in_grid(g, nx, ny, nz)) continue;
+    const long long nv = fb_ii(g, nx, ny, nz);
+    const unsigned o = ord[nv];
+    uint32_t c;
+    if (o != XNONE) { if (o < i) c = nc_in[o]; else continue; }
+    else c = cobs[nv] & FB_CODE_MASK;
+    if (c >= 2u) {
+      int ox, oy, oz; fb_unpack(c, ox, oy, oz);
+      const long long oi = fb_ii(g, ox, oy, oz);
+      if ((occbits[oi >> 5] >> (oi & 31)) & 1u) { res = c; break; }             // Exist(closest obstacle) (:312), then `break` (:319)
+    }
+  }
+  nc_out[i] = res;
+  if (res != nc_in[i]) *changed = 1u;
+}
+__global__ void k_x_apply_reseed(const uint32_t *deps, unsigned n, const uint32_t *nc, uint32_t *cobs, unsigned long long *LS,
+                                 unsigned long long t0, uint8_t *flags) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  cobs[deps[i]] = nc[i];
+  LS[deps[i]] = t0 + i;                                        // InsertIntoList(new_obs_idx, obs_idx) (:333)
+  flags[i] = nc[i] >= 2u;                                      // `if (distance < infinity_) update_queue_.push` (:329-331)
+}
+__global__ void k_x_set_M(const uint32_t *E, unsigned first, unsigned n, uint32_t *M) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) M[E[first + i]] = first + i;
+}
+
+// ------------------------------------------------------------------ E3: relax, one FIFO generation at a time
+__global__ void k_x_init_beh(const uint32_t *E, unsigned n, const uint32_t *cobs, unsigned long long *B) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) B[i] = (X_PUSH << 32) | (cobs[E[i]] & FB_CODE_MASK);
+}
+__global__ void k_x_eval(FbGeom g, const uint32_t *E, unsigned n, const uint32_t *cobs, const uint32_t *M, const unsigned long long *Bin,
+                         unsigned long long *Bout, unsigned *changed) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int x, y, z; x_coords(g, E[i], x, y, z);
+  const unsigned T0 = i * 32u;
+  const XState s = x_state(g, cobs, M, Bin, x, y, z, T0);
+  const uint32_t c0 = cobs[E[i]] & FB_CODE_MASK;
+  unsigned long long nb;
+  if (s.d != x_dist_of(x, y, z, c0)) nb = X_DEAD << 32;       // `xx.distance_ != distance_buffer_[idx]`: stale (:345)
+  else {
+    unsigned curd = s.d; uint32_t curc = s.c; bool ch = false;
+    for (int k = 0; k < 24; ++k) {                             // pull phase (:349-367)
+      const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
+      if (!fb_in_range(g, nx, ny, nz) || !fb_in_grid(g, nx, ny, nz)) continue;
+      const XState sn = x_state(g, cobs, M, Bin, nx, ny, nz, T0);
+      if (sn.c < 2u) continue;
+      const unsigned t = x_d2(x, y, z, sn.c);
+      if (curd > t) { curd = t; curc = sn.c; ch = true; }
+    }
+    nb = ch ? ((X_PULL << 32) | curc) : ((X_PUSH << 32) | s.c);
+  }
+  Bout[i] = nb;
+  if (nb != Bin[i]) *changed = 1u;
+}
+// Final writes of the generation -> slots (timestamp order) of the next generation's queue.
+__global__ void k_x_commit(FbGeom g, const uint32_t *E, unsigned n, const uint32_t *cobs, const uint32_t *M, const unsigned long long *B,
+                           uint32_t *slotv, uint32_t *slotc, uint8_t *slotf, unsigned long long *expansions) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n && (B[i] >> 32) != X_DEAD;
+  const unsigned nlive = __popc(__ballot_sync(0xffffffffu, live));
+  if ((threadIdx.x & 31) == 0 && nlive) atomicAdd(expansions, (unsigned long long)nlive);   // `times++` (:347)
+  if (!live) return;
+  int x, y, z; x_coords(g, E[i], x, y, z);
+  const unsigned long long b = B[i];
+  if ((b >> 32) == X_PUSH) {
+    for (int k = 0; k < 24; ++k) {                             // push phase (:375-391)
+      const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
+      if (!fb_in_range(g, nx, ny, nz) || !fb_in_grid(g, nx, ny, nz)) continue;
+      const XState f = x_state(g, cobs, M, B, nx, ny, nz, XNONE);
+      const unsigned ts = i * 32u + (unsigned)k;
+      if (f.ts == ts) { slotv[ts] = (uint32_t)fb_ii(g, nx, ny, nz); slotc[ts] = f.c; slotf[ts] = 1; }
+    }
+  } else {
+    const XState f = x_state(g, cobs, M, B, x, y, z, XNONE);
+    const unsigned ts = i * 32u + 24u;
+    if (f.ts == ts) { slotv[ts] = E[i]; slotc[ts] = f.c; slotf[ts] = 1; }
+  }
+}
+__global__ void k_x_clear_M(const uint32_t *E, unsigned n, uint32_t *M) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) M[E[i]] = XNONE;
+}
+__global__ void k_x_apply(const uint32_t *sel, unsigned n, const uint32_t *slotv, const uint32_t *slotc, uint32_t *cobs, uint32_t *M,
+                          unsigned long long *LS, unsigned long long t0, uint32_t *Enext) {
+  const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint32_t s = sel[r], v = slotv[s];
+  cobs[v] = slotc[s];
+  LS[v] = t0 + s;                                              // every accepted write relinks the voxel at its list's front
+  M[v] = r;
+  Enext[r] = v;
+}
+__global__ void k_x_fill32(uint32_t *a, size_t n, uint32_t val) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] = val;
+}
+__global__ void k_x_fill64(unsigned long long *a, size_t n, unsigned long long val) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] = val;
+}
+
+// ================================================================== host side
+#define XCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { snprintf(X->err, sizeof(X->err), "%s: %s", #call, cudaGetErrorString(e__)); return e__; } } while (0)
+static inline unsigned nblk(size_t n, unsigned t = 256) { return (unsigned)((n + t - 1) / t); }
+
+template <typename T>
+static cudaError_t x_ensure(FbExact *X, T **p, size_t *cap, size_t need) {
+  if (need <= *cap) return cudaSuccess;
+  size_t nc = need + need / 2 + 4096;
+  T *np = nullptr;
+  XCK(cudaMalloc((void **)&np, nc * sizeof(T)));
+  if (*p) cudaFree(*p);
+  *p = np; *cap = nc;
+  return cudaSuccess;
+}
+static cudaError_t x_tmp(FbExact *X, size_t bytes) {
+  if (bytes <= X->cub_bytes) return cudaSuccess;
+  if (X->cub_tmp) cudaFree(X->cub_tmp);
+  X->cub_bytes = bytes + bytes / 2 + (1u << 20);
+  XCK(cudaMalloc(&X->cub_tmp, X->cub_bytes));
+  return cudaSuccess;
+}
+// ordered compaction: out[0..count) = in[i] for flags[i] != 0, order kept
+static cudaError_t x_select(FbExact *X, const uint32_t *in, const uint8_t *flags, uint32_t *out, unsigned n, unsigned *count, cudaStream_t s) {
+  *count = 0;
+  if (n == 0) return cudaSuccess;
+  size_t bytes = 0;
+  XCK(cub::DeviceSelect::Flagged(nullptr, bytes, in, flags, out, X->d_count, (int)n, s));
+  cudaError_t e = x_tmp(X, bytes); if (e) return e;
+  XCK(cub::DeviceSelect::Flagged(X->cub_tmp, bytes, in, flags, out, X->d_count, (int)n, s));
+  XCK(cudaMemcpyAsync(X->h_count, X->d_count, 4, cudaMemcpyDeviceToHost, s));
+  XCK(cudaStreamSynchronize(s));
+  *count = *X->h_count;
+  return cudaSuccess;
+}
+static cudaError_t x_sort_pairs(FbExact *X, const unsigned long long *kin, unsigned long long *kout, const uint32_t *vin, uint32_t *vout, unsigned n, cudaStream_t s) {
+  size_t bytes = 0;
+  XCK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, 64, s));
+  cudaError_t e = x_tmp(X, bytes); if (e) return e;
+  XCK(cub::DeviceRadixSort::SortPairs(X->cub_tmp, bytes, kin, kout, vin, vout, (int)n, 0, 64, s));
+  return cudaSuccess;
+}
+static cudaError_t x_flag(FbExact *X, cudaStream_t s, unsigned *out) {   // read-and-clear the device "changed" flag
+  XCK(cudaMemcpyAsync(X->h_count, X->d_flag, 4, cudaMemcpyDeviceToHost, s));
+  XCK(cudaMemsetAsync(X->d_flag, 0, 4, s));
+  XCK(cudaStreamSynchronize(s));
+  *out = *X->h_count;
+  return cudaSuccess;
+}
+
+cudaError_t fb_exact_init(FbExact *X, const FbGeom &g, cudaStream_t s) {
+  memset(X, 0, sizeof(*X));
+  const size_t P = (size_t)g.ptotal;
+  XCK(cudaMalloc((void **)&X->M, P * 4)); XCK(cudaMalloc((void **)&X->LS, P * 8)); XCK(cudaMalloc((void **)&X->tkey, P * 8));
+  XCK(cudaMalloc((void **)&X->touched, P * 4));
+  XCK(cudaMalloc((void **)&X->d_count, 16)); XCK(cudaMalloc((void **)&X->d_flag, 16));
+  XCK(cudaMallocHost((void **)&X->h_count, 16));
+  XCK(cudaMemsetAsync(X->d_count, 0, 16, s)); XCK(cudaMemsetAsync(X->d_flag, 0, 16, s));
+  k_x_fill32<<<148 * 8, 256, 0, s>>>(X->M, P, XNONE);
+  k_x_fill64<<<148 * 8, 256, 0, s>>>(X->tkey, P, ~0ull);
+  XCK(cudaMemsetAsync(X->LS, 0, P * 8, s));
+  X->tclock = 1; X->key_base = 0;
+  return cudaGetLastError();
+}
+void fb_exact_free(FbExact *X) {
+  void *p[] = {X->M, X->LS, X->tkey, X->touched, X->d_count, X->d_flag, X->E[0], X->E[1], X->B[0], X->B[1], X->slotv, X->slotc, X->slotf, X->sel,
+               X->k1, X->k2, X->k1b, X->k2b, X->dv, X->idx[0], X->idx[1], X->deps, X->nc[0], X->nc[1], X->flags, X->flags2, X->cub_tmp};
+  for (void *q : p) if (q) cudaFree(q);
+  if (X->h_count) cudaFreeHost(X->h_count);
+  memset(X, 0, sizeof(*X));
+}
+
+// UpdateOccupancy in first-observation order.  touched[0..n) = voxels with pending observations (any order).
+cudaError_t fb_exact_update_occupancy(FbExact *X, const FbGeom &g, unsigned n, unsigned long long *cnt, double *occ, uint32_t *cobs, uint32_t *occbits,
+                                      uint32_t **ins, size_t *cap_ins, unsigned *n_ins, uint32_t **del, size_t *cap_del, unsigned *n_del,
+                                      int global_map, const double L[5], cudaStream_t s, int *launches) {
+  if (n == 0) return cudaSuccess;
+  cudaError_t e;
+  if ((e = x_ensure(X, &X->k1, &X->cap_k1, n))) return e;
+  if ((e = x_ensure(X, &X->k1b, &X->cap_k1b, n))) return e;
+  if ((e = x_ensure(X, &X->deps, &X->cap_deps, n))) return e;
+  if ((e = x_ensure(X, &X->flags, &X->cap_flags, n))) return e;
+  if ((e = x_ensure(X, &X->flags2, &X->cap_flags2, n))) return e;
+  k_x_gather_keys<<<nblk(n), 256, 0, s>>>(X->touched, n, X->tkey, X->k1);
+  if ((e = x_sort_pairs(X, X->k1, X->k1b, X->touched, X->deps, n, s))) return e;
+  k_x_integrate<<<nblk(n), 256, 0, s>>>(g, X->deps, n, cnt, occ, cobs, occbits, X->tkey, X->flags, X->flags2, global_map, L[0], L[1], L[2], L[3], L[4]);
+  *launches += 3;
+  // append to the queues, order kept
+  {   // grow the queues if needed (contents kept)
+    for (int q = 0; q < 2; ++q) {
+      uint32_t **lst = q ? del : ins; size_t *cap = q ? cap_del : cap_ins; const unsigned have = q ? *n_del : *n_ins;
+      if ((size_t)have + n > *cap) {
+        size_t nc = (size_t)have + n + ((size_t)have + n) / 2 + 4096;
+        uint32_t *np = nullptr;
+        XCK(cudaMalloc((void **)&np, nc * 4));
+        if (*lst && have) XCK(cudaMemcpyAsync(np, *lst, (size_t)have * 4, cudaMemcpyDeviceToDevice, s));
+        XCK(cudaStreamSynchronize(s));
+        if (*lst) cudaFree(*lst);
+        *lst = np; *cap = nc;
+      }
+    }
+  }
+  unsigned c = 0;
+  if ((e = x_select(X, X->deps, X->flags, *ins + *n_ins, n, &c, s))) return e;
+  *n_ins += c;
+  if ((e = x_select(X, X->deps, X->flags2, *del + *n_del, n, &c, s))) return e;
+  *n_del += c;
+  return cudaSuccess;
+}
+
+cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, uint32_t *scratch, const double *occ, const uint32_t *occbits, double l_occ,
+                                 const uint32_t *ins, unsigned n_ins, const uint32_t *del, unsigned n_del, cudaStream_t s, FbExactStats *st, int *launches) {
+  cudaError_t e;
+  const size_t P = (size_t)g.ptotal;
+  memset(st, 0, sizeof(*st));
+  if ((e = x_ensure(X, &X->flags, &X->cap_flags, (size_t)(n_ins > n_del ? n_ins : n_del) + 16))) return e;
+  if ((e = x_ensure(X, &X->E[0], &X->cap_E[0], (size_t)n_ins + 16))) return e;
+  // ---- E1: insert seeds in insert_queue_ order (:278-291)
+  unsigned nE = 0;
+  if (n_ins) {
+    k_x_flag_exist<<<nblk(n_ins), 256, 0, s>>>(ins, n_ins, occ, l_occ, X->flags, 1);
+    if ((e = x_select(X, ins, X->flags, X->E[0], n_ins, &nE, s))) return e;
+    if (nE) k_x_apply_seed<<<nblk(nE), 256, 0, s>>>(g, X->E[0], nE, cobs, X->M, X->LS, X->tclock);
+    X->tclock += nE;
+    *launches += 2;
+  }
+  // ---- E2: deletes (:292-337)
+  if (n_del) {
+    if ((e = x_ensure(X, &X->sel, &X->cap_sel, (size_t)n_del + 16))) return e;
+    k_x_fill32<<<148 * 8, 256, 0, s>>>(scratch, P, XNONE);
+    k_x_del_minpos<<<nblk(n_del), 256, 0, s>>>(del, n_del, occ, l_occ, scratch);
+    k_x_del_flag<<<nblk(n_del), 256, 0, s>>>(del, n_del, occ, l_occ, scratch, X->flags);
+    unsigned nd = 0;
+    if ((e = x_select(X, del, X->flags, X->sel, n_del, &nd, s))) return e;
+    *launches += 3;
+    if (nd) {
+      k_x_fill32<<<148 * 8, 256, 0, s>>>(scratch, P, XNONE);
+      k_x_del_rank<<<nblk(nd), 256, 0, s>>>(X->sel, nd, scratch);
+      // dependants: the list is sized by a first counting attempt, then (rarely) re-run with more room
+      unsigned ndep = 0;
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        size_t cap = X->cap_dv;
+        XCK(cudaMemsetAsync(X->d_count, 0, 4, s));
+        k_x_scan_deps<<<148 * 16, 256, 0, s>>>(g, cobs, scratch, X->LS, X->k1, X->k2, X->dv, X->d_count, (unsigned)((cap < X->cap_k1 ? cap : X->cap_k1) < X->cap_k2 ? (cap < X->cap_k1 ? cap : X->cap_k1) : X->cap_k2));
+        XCK(cudaMemcpyAsync(X->h_count, X->d_count, 4, cudaMemcpyDeviceToHost, s));
+        XCK(cudaStreamSynchronize(s));
+        ndep = *X->h_count;
+        *launches += 1;
+        if (ndep <= cap && ndep <= X->cap_k1 && ndep <= X->cap_k2) break;
+        if ((e = x_ensure(X, &X->dv, &X->cap_dv, ndep))) return e;
+        if ((e = x_ensure(X, &X->k1, &X->cap_k1, ndep))) return e;
+        if ((e = x_ensure(X, &X->k2, &X->cap_k2, ndep))) return e;
+      }
+      st->dependants = ndep;
+      if (ndep) {
+        if ((e = x_ensure(X, &X->k1b, &X->cap_k1b, ndep))) return e;
+        if ((e = x_ensure(X, &X->k2b, &X->cap_k2b, ndep))) return e;
+        if ((e = x_ensure(X, &X->idx[0], &X->cap_idx[0], ndep))) return e;
+        if ((e = x_ensure(X, &X->idx[1], &X->cap_idx[1], ndep))) return e;
+        if ((e = x_ensure(X, &X->deps, &X->cap_deps, ndep))) return e;
+        if ((e = x_ensure(X, &X->nc[0], &X->cap_nc[0], ndep))) return e;
+        if ((e = x_ensure(X, &X->nc[1], &X->cap_nc[1], ndep))) return e;
+        if ((e = x_ensure(X, &X->flags, &X->cap_flags, ndep))) return e;
+        // order = (obstacle's position in delete_queue_, link time descending): two stable radix sorts
+        k_x_iota<<<nblk(ndep), 256, 0, s>>>(X->idx[0], ndep);
+        if ((e = x_sort_pairs(X, X->k2, X->k2b, X->idx[0], X->idx[1], ndep, s))) return e;
+        k_x_gather64<<<nblk(ndep), 256, 0, s>>>(X->k1, X->idx[1], ndep, X->k1b);
+        if ((e = x_sort_pairs(X, X->k1b, X->k2b, X->idx[1], X->idx[0], ndep, s))) return e;
+        k_x_gather32<<<nblk(ndep), 256, 0, s>>>(X->dv, X->idx[0], ndep, X->deps);
+        k_x_fill32<<<148 * 8, 256, 0, s>>>(scratch, P, XNONE);
+        k_x_set_ord<<<nblk(ndep), 256, 0, s>>>(X->deps, ndep, scratch, X->nc[0]);
+        *launches += 8;
+        int cur = 0;
+        for (int it = 0; it < 100000; ++it) {
+          k_x_reseed<<<nblk(ndep), 256, 0, s>>>(g, X->deps, ndep, cobs, scratch, occbits, X->nc[cur], X->nc[cur ^ 1], X->d_flag);
+          *launches += 1;
+          cur ^= 1;
+          unsigned ch = 0;
+          if ((e = x_flag(X, s, &ch))) return e;
+          st->reseed_rounds++;
+          if (!ch) break;
+        }
+        k_x_apply_reseed<<<nblk(ndep), 256, 0, s>>>(X->deps, ndep, X->nc[cur], cobs, X->LS, X->tclock, X->flags);
+        X->tclock += ndep;
+        if ((e = x_ensure(X, &X->E[1], &X->cap_E[1], (size_t)nE + ndep + 16))) return e;   // E[0] may be too small: rebuild in E[1]
+        if (nE) XCK(cudaMemcpyAsync(X->E[1], X->E[0], (size_t)nE * 4, cudaMemcpyDeviceToDevice, s));
+        unsigned nr = 0;
+        if ((e = x_select(X, X->deps, X->flags, X->E[1] + nE, ndep, &nr, s))) return e;
+        if (nr) k_x_set_M<<<nblk(nr), 256, 0, s>>>(X->E[1], nE, nr, X->M);
+        // keep the generation-0 list in E[0]
+        if ((e = x_ensure(X, &X->E[0], &X->cap_E[0], (size_t)nE + nr + 16))) return e;
+        XCK(cudaMemcpyAsync(X->E[0], X->E[1], (size_t)(nE + nr) * 4, cudaMemcpyDeviceToDevice, s));
+        nE += nr;
+        *launches += 3;
+      }
+    }
+  }
+  // ---- E3: relax (:338-392)
+  int cur = 0;
+  XCK(cudaMemsetAsync(X->d_count + 2, 0, 8, s));               // expansions counter (u64 at d_count[2..3])
+  while (nE) {
+    st->generations++;
+    const size_t nslots = (size_t)nE * 32;
+    if (nE >= (1u << 27)) { snprintf(X->err, sizeof(X->err), "exact mode: generation with more than 2^27 entries"); return cudaErrorInvalidValue; }
+    if ((e = x_ensure(X, &X->B[0], &X->cap_B[0], nE))) return e;
+    if ((e = x_ensure(X, &X->B[1], &X->cap_B[1], nE))) return e;
+    if ((e = x_ensure(X, &X->slotv, &X->cap_slotv, nslots))) return e;
+    if ((e = x_ensure(X, &X->slotc, &X->cap_slotc, nslots))) return e;
+    if ((e = x_ensure(X, &X->slotf, &X->cap_slotf, nslots))) return e;
+    if ((e = x_ensure(X, &X->sel, &X->cap_sel, nslots))) return e;
+    k_x_init_beh<<<nblk(nE), 256, 0, s>>>(X->E[cur], nE, cobs, X->B[0]);
+    int b = 0;
+    for (int it = 0; it < 100000; ++it) {
+      k_x_eval<<<nblk(nE, 128), 128, 0, s>>>(g, X->E[cur], nE, cobs, X->M, X->B[b], X->B[b ^ 1], X->d_flag);
+      *launches += 1;
+      b ^= 1;
+      unsigned ch = 0;
+      if ((e = x_flag(X, s, &ch))) return e;
+      st->eval_rounds++;
+      if (!ch) break;
+    }
+    XCK(cudaMemsetAsync(X->slotf, 0, nslots, s));
+    k_x_commit<<<nblk(nE, 128), 128, 0, s>>>(g, X->E[cur], nE, cobs, X->M, X->B[b], X->slotv, X->slotc, X->slotf, (unsigned long long *)(X->d_count + 2));
+    k_x_clear_M<<<nblk(nE), 256, 0, s>>>(X->E[cur], nE, X->M);
+    unsigned n2 = 0;
+    {
+      size_t bytes = 0;
+      cub::CountingInputIterator<uint32_t> it0(0);
+      XCK(cub::DeviceSelect::Flagged(nullptr, bytes, it0, X->slotf, X->sel, X->d_count, (int)nslots, s));
+      if ((e = x_tmp(X, bytes))) return e;
+      XCK(cub::DeviceSelect::Flagged(X->cub_tmp, bytes, it0, X->slotf, X->sel, X->d_count, (int)nslots, s));
+      XCK(cudaMemcpyAsync(X->h_count, X->d_count, 4, cudaMemcpyDeviceToHost, s));
+      XCK(cudaStreamSynchronize(s));
+      n2 = *X->h_count;
+    }
+    if ((e = x_ensure(X, &X->E[cur ^ 1], &X->cap_E[cur ^ 1], (size_t)n2 + 16))) return e;
+    if (n2) k_x_apply<<<nblk(n2), 256, 0, s>>>(X->sel, n2, X->slotv, X->slotc, cobs, X->M, X->LS, X->tclock, X->E[cur ^ 1]);
+    *launches += 5;
+    X->tclock += nslots + 1;
+    st->voxels_changed += n2;
+    cur ^= 1;
+    nE = n2;
+  }
+  XCK(cudaMemcpyAsync(X->h_count, X->d_count + 2, 8, cudaMemcpyDeviceToHost, s));
+  XCK(cudaStreamSynchronize(s));
+  st->expansions = *(unsigned long long *)X->h_count;
+  return cudaSuccess;
+}

@@ -11,6 +11,7 @@
 #include <new>
 #include "../../include/fiesta_b200.h"
 #include "fb_common.cuh"
+#include "fb_exact.h"
 
 static thread_local std::string g_last_error;
 static void set_error(const char *fmt, const char *a = "", const char *b = "") {
@@ -58,6 +59,9 @@ struct fiesta_map {
   double *d_qin, *d_qout; size_t cap_q;
   cudaEvent_t ev[4];
   unsigned long long *d_dbg;
+  int mode;
+  FbExact X;
+  unsigned n_xtouched;
   fiesta_stats st;
 };
 
@@ -75,16 +79,16 @@ __global__ void k_reset_esdf_ctr(FbCounters *c) {
 }
 __global__ void k_reset_touched(FbCounters *c) { c->n_touched = 0; }
 __global__ void k_reset_queues(FbCounters *c, int touched, int insdel) {
-  if (touched) c->n_touch_tiles = 0;
+  if (touched) { c->n_touch_tiles = 0; c->n_xtouched = 0; }
   if (insdel) c->n_ins = c->n_del = 0;
 }
 
 // O1 counter part for per-call SetOccupancy events staged on the host (ESDFMap.cpp:424-435).
-__global__ void k_apply_events(FbGeom g, const uint32_t *ev, size_t n, FbTouch t) {
+__global__ void k_apply_events(FbGeom g, const uint32_t *ev, size_t n, FbTouch t, unsigned long long key_base) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t e = ev[i];
-  fb_touch(g, t, e & 0x7fffffffu, e >> 31);
+  fb_touch(g, t, e & 0x7fffffffu, e >> 31, key_base + i);       // the i-th staged call = its position in the serial order
 }
 
 // O2: ESDFMap::UpdateOccupancy (ESDFMap.cpp:235-271).  One 128-thread CTA streams the counters of one queued 8^3 tile
@@ -258,14 +262,16 @@ static int ensure(T **ptr, size_t *cap, size_t need, bool keep, cudaStream_t s) 
 static int fetch_counters(fiesta_map *m) {
   CK(cudaMemcpyAsync(m->h_ctr, m->d_ctr, sizeof(FbCounters), cudaMemcpyDeviceToHost, m->stream));
   CK(cudaStreamSynchronize(m->stream));
-  m->n_touch_tiles = m->h_ctr->n_touch_tiles; m->n_ins = m->h_ctr->n_ins; m->n_del = m->h_ctr->n_del;
+  m->n_touch_tiles = m->h_ctr->n_touch_tiles; m->n_xtouched = m->h_ctr->n_xtouched;
+  if (m->mode == FIESTA_MODE_FAST) { m->n_ins = m->h_ctr->n_ins; m->n_del = m->h_ctr->n_del; }
   return FIESTA_OK;
 }
 static int flush_events(fiesta_map *m) {
   if (m->n_ev == 0) return FIESTA_OK;
   CK(cudaMemcpyAsync(m->d_ev, m->h_ev, m->n_ev * sizeof(uint32_t), cudaMemcpyHostToDevice, m->stream));
-  FbTouch t = {m->cnt, m->touch_flag, m->touch_list, m->touch_epoch, m->d_ctr};
-  k_apply_events<<<(unsigned)((m->n_ev + 255) / 256), 256, 0, m->stream>>>(m->g, m->d_ev, m->n_ev, t);
+  FbTouch t = {m->cnt, m->touch_flag, m->touch_list, m->touch_epoch, m->d_ctr, m->mode == FIESTA_MODE_EXACT ? m->X.tkey : nullptr, m->X.touched};
+  k_apply_events<<<(unsigned)((m->n_ev + 255) / 256), 256, 0, m->stream>>>(m->g, m->d_ev, m->n_ev, t, m->X.key_base);
+  m->X.key_base += m->n_ev;
   m->st.kernel_launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(m->stream));                                   // the pinned buffer is reused immediately
@@ -300,6 +306,8 @@ void fiesta_destroy(fiesta_map *m) {
                  m->changed[0], m->changed[1], m->changed_bbox[0], m->changed_bbox[1], m->touch_flag, m->touch_list, m->ins, m->del, m->d_ctr, m->d_ev,
                  m->d_xyz, m->ray_list, m->ray_len, m->ray_reach, m->ray_act, m->ray_dirty, m->d_qin, m->d_qout};
   for (void *p : dev) if (p) cudaFree(p);
+  if (m->mode == FIESTA_MODE_EXACT) fb_exact_free(&m->X);
+  if (m->d_dbg) cudaFree(m->d_dbg);
   if (m->h_ctr) cudaFreeHost(m->h_ctr);
   if (m->h_ev) cudaFreeHost(m->h_ev);
   for (int i = 0; i < 4; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
@@ -323,6 +331,7 @@ int fiesta_create(const fiesta_config *cfg, fiesta_map **out) {
   if (!m) { set_error("out of host memory"); return FIESTA_ERR_INVALID; }
   memset((void *)m, 0, sizeof(*m));
   m->device = cfg->device;
+  m->mode = cfg->mode == FIESTA_MODE_EXACT ? FIESTA_MODE_EXACT : FIESTA_MODE_FAST;
   FbGeom &g = m->g;
   int gs[3];
   for (int i = 0; i < 3; ++i) {                                           // ctor, ESDFMap.cpp:171-186
@@ -388,6 +397,7 @@ int fiesta_create(const fiesta_config *cfg, fiesta_map **out) {
   m->wf_blocks = fb_esdf_wavefront_blocks(m->device);
   m->rr_blocks = fb_ray_resolve_blocks(m->device);
   if (m->wf_blocks <= 0 || m->rr_blocks <= 0) { set_error("cooperative kernels do not fit on this device"); fiesta_destroy(m); return FIESTA_ERR_CUDA; }
+  if (m->mode == FIESTA_MODE_EXACT && fb_exact_init(&m->X, g, m->stream) != cudaSuccess) { set_error("exact mode init: %s", m->X.err); fiesta_destroy(m); return FIESTA_ERR_CUDA; }
   CKD(cudaStreamSynchronize(m->stream));
 #undef CKD
   *out = m;
@@ -511,6 +521,8 @@ int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, co
   if ((r = ensure(&m->ray_list, &m->cap_ray_list, (size_t)a.cap * (size_t)n, false, m->stream))) return r;
   a.cnt = m->cnt; a.stamp[0] = m->stamp[0]; a.stamp[1] = m->stamp[1];
   a.touch_flag = m->touch_flag; a.touch_list = m->touch_list; a.touch_epoch = m->touch_epoch;
+  a.tkey = m->mode == FIESTA_MODE_EXACT ? m->X.tkey : nullptr; a.xtouched = m->X.touched; a.key_base = m->X.key_base;
+  m->X.key_base += 1ull << 30;
   a.ray_list = m->ray_list; a.ray_len = m->ray_len; a.ray_reach = m->ray_reach; a.ray_act = m->ray_act; a.ray_dirty = m->ray_dirty; a.ctr = m->d_ctr;
   CK(cudaEventRecord(m->ev[0], m->stream));
   k_reset_ray_ctr<<<1, 1, 0, m->stream>>>(m->d_ctr);
@@ -538,7 +550,7 @@ int fiesta_raycast_frame(fiesta_map *m, const float *xyz, int64_t n, const doubl
 
 int fiesta_check_update(fiesta_map *m) {
   if (!m) return 0;
-  return (m->n_ev > 0 || m->n_touch_tiles > 0) ? 1 : 0;                       // !occupancy_queue_.empty(), ESDFMap.cpp:229
+  return (m->n_ev > 0 || m->n_touch_tiles > 0 || m->n_xtouched > 0) ? 1 : 0;                       // !occupancy_queue_.empty(), ESDFMap.cpp:229
 }
 
 int fiesta_update_occupancy(fiesta_map *m, int global_map) {
@@ -549,6 +561,23 @@ int fiesta_update_occupancy(fiesta_map *m, int global_map) {
   cudaEventRecord(m->ev[0], m->stream);
   if ((r = flush_events(m))) return -r;
   if ((r = fetch_counters(m))) return -r;
+  if (m->mode == FIESTA_MODE_EXACT) {
+    const unsigned nx = m->n_xtouched;
+    m->st.occupancy_updates = nx;
+    if (nx) {
+      const double L[5] = {m->l_hit, m->l_miss, m->l_min, m->l_max, m->l_occ};
+      int launches = 0;
+      if (fb_exact_update_occupancy(&m->X, m->g, nx, m->cnt, m->occ, m->cobs, m->occbits, &m->ins, &m->cap_ins, &m->n_ins, &m->del, &m->cap_del,
+                                    &m->n_del, global_map, L, m->stream, &launches) != cudaSuccess) { set_error("exact UpdateOccupancy: %s", m->X.err); return -FIESTA_ERR_CUDA; }
+      k_reset_queues<<<1, 1, 0, m->stream>>>(m->d_ctr, 1, 0);
+      m->st.kernel_launches += launches + 1;
+    }
+    cudaEventRecord(m->ev[1], m->stream);
+    if ((r = fetch_counters(m))) return -r;
+    cudaEventElapsedTime(&m->st.ms_update_occupancy, m->ev[0], m->ev[1]);
+    m->st.touched_voxels = 0;
+    return (m->n_ins > 0 || m->n_del > 0) ? 1 : 0;
+  }
   const unsigned n = m->n_touch_tiles;
   m->st.occupancy_updates = 0;
   if (n) {
@@ -575,9 +604,24 @@ int fiesta_update_esdf(fiesta_map *m) {
   if (!m) return FIESTA_ERR_INVALID;
   CK(cudaSetDevice(m->device));
   m->st.inserts = m->n_ins; m->st.deletes = m->n_del;
-  m->st.voxels_changed = m->st.voxels_reset = m->st.tile_visits = m->st.generations = 0;
+  m->st.voxels_changed = m->st.voxels_reset = m->st.tile_visits = m->st.generations = m->st.expansions = 0;
   m->st.ms_update_esdf = m->st.ms_esdf_delete_scan = m->st.ms_esdf_wavefront = 0;
   if (m->n_ins == 0 && m->n_del == 0) return FIESTA_OK;
+  if (m->mode == FIESTA_MODE_EXACT) {
+    FbExactStats xs;
+    int launches = 0;
+    CK(cudaEventRecord(m->ev[0], m->stream));
+    if (fb_exact_update_esdf(&m->X, m->g, m->cobs, m->cobs_b, m->occ, m->occbits, m->l_occ, m->ins, m->n_ins, m->del, m->n_del, m->stream, &xs,
+                             &launches) != cudaSuccess) { set_error("exact UpdateESDF: %s", m->X.err); return FIESTA_ERR_CUDA; }
+    CK(cudaEventRecord(m->ev[3], m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    CK(cudaEventElapsedTime(&m->st.ms_update_esdf, m->ev[0], m->ev[3]));
+    m->st.kernel_launches += launches;
+    m->st.voxels_changed = (int64_t)xs.voxels_changed; m->st.expansions = (int64_t)xs.expansions; m->st.voxels_reset = xs.dependants;
+    m->st.generations = xs.generations; m->st.tile_visits = 0;
+    m->n_ins = m->n_del = 0;
+    return FIESTA_OK;
+  }
   FbEsdfArgs a;
   a.cobs = m->cobs; a.cobs_b = m->cobs_b; a.occ = m->occ; a.occbits = m->occbits; a.tile_flag = m->tile_flag; a.nb_flag = m->nb_flag;
   for (int k = 0; k < 2; ++k) { a.list[k] = m->list[k]; a.changed[k] = m->changed[k]; a.changed_bbox[k] = m->changed_bbox[k]; }

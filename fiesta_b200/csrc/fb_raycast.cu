@@ -79,9 +79,11 @@ __device__ __forceinline__ int fb_endpoint(const FbRayArgs &a, long long i, doub
   return 1;
 }
 
-__device__ __forceinline__ void fb_count(const FbGeom &g, const FbRayArgs &a, long long ii, unsigned occ) {
-  FbTouch t = {a.cnt, a.touch_flag, a.touch_list, a.touch_epoch, a.ctr};
-  fb_touch(g, t, (unsigned)ii, occ);
+// sub = 0 for the endpoint observation of point i, 1 + t for the free-space observation at back-walk position t: the serial
+// reference makes them in exactly this order (Fiesta.h:213-215, then :239-276).
+__device__ __forceinline__ void fb_count(const FbGeom &g, const FbRayArgs &a, long long ii, unsigned occ, unsigned long long i, unsigned sub) {
+  FbTouch t = {a.cnt, a.touch_flag, a.touch_list, a.touch_epoch, a.ctr, a.tkey, a.xtouched};
+  fb_touch(g, t, (unsigned)ii, occ, a.key_base + (i << 11) + sub);
 }
 
 // ---------------------------------------------------------------- endpoints
@@ -97,7 +99,7 @@ __global__ void k_ray_endpoints(FbGeom g, FbRayArgs a) {
     if (fb_pos_to_vox(g, px, py, pz, vx, vy, vz)) {
       long long ii; bool in_range;
       if (fb_resolve_vox(g, vx, vy, vz, ii, in_range)) {
-        if (in_range) fb_count(g, a, ii, kind == 1 ? 1u : 0u);
+        if (in_range) fb_count(g, a, ii, kind == 1 ? 1u : 0u, (unsigned long long)i, 0u);
         // set_occ_ ownership: lowest point index wins (Fiesta.h:227-230)
         atomicMax(&a.stamp[1][ii], (a.owner_tag << FB_RAY_BITS) | (FB_RAY_MASK - (unsigned)i));
       }
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_ray_resolve(FbGeom g, FbRayAr
       const int t = t0 + (int)lane;
       bool cnt = false; unsigned ii = 0;
       if (t < R) { const unsigned e = __ldcg(&row[L - 1 - t]); cnt = (e >> 30) == FB_CLS_COUNT; ii = e & FB_LIST_IDX_MASK; }
-      if (cnt) fb_count(g, a, ii, 0u);
+      if (cnt) fb_count(g, a, ii, 0u, (unsigned long long)i, 1u + (unsigned)t);
     }
   }
 }

@@ -33,13 +33,23 @@ enum {
   FIESTA_ERR_LIMIT = 4      /* grid or frame exceeds a documented limit */
 };
 
+/* Ordering mode of UpdateOccupancy / UpdateESDF.
+ *  FAST : order-free parallel wavefront.  Occupancy, counters and queries are bit-exact; distance_ is bit-exact wherever the
+ *         reference's result does not depend on its FIFO arrival order (every fully observed scene); exact distance ties keep
+ *         the smallest obstacle coordinate instead of the first arrival.
+ *  EXACT: reproduces the reference's sequential FIFO order on the device (insert/delete queue order, LIFO dependant lists,
+ *         dirs_ order, intra-queue visibility): closest_obstacle_ and distance_ equal the reference bit for bit in every
+ *         scene, and the expansion count equals the reference's "Expanding N nodes".  Several times slower than FAST. */
+enum { FIESTA_MODE_FAST = 0, FIESTA_MODE_EXACT = 1 };
+
 /* ESDFMap::ESDFMap(origin, resolution, map_size) arguments (ESDFMap.h:116, ESDFMap.cpp:171-213) plus placement. */
 typedef struct fiesta_config {
   double origin[3];     /* l_cornor_ : lower corner of the map, metres */
   double resolution;    /* voxel edge, metres */
   double map_size[3];   /* r_cornor_ - l_cornor_, metres; grid = ceil(map_size / resolution) */
   int32_t device;       /* CUDA device ordinal */
-  int32_t reserved[7];  /* must be zero */
+  int32_t mode;         /* FIESTA_MODE_FAST (0) or FIESTA_MODE_EXACT (1), see below */
+  int32_t reserved[6];  /* must be zero */
 } fiesta_config;
 
 /* Fiesta::RaycastProcess parameters (parameters.h:148-149, Fiesta.h:209-245). */
@@ -53,6 +63,7 @@ typedef struct fiesta_stats {
   int64_t occupancy_updates;   /* occupancy_queue_ size drained by the last UpdateOccupancy          (:237) */
   int64_t inserts, deletes;    /* insert_queue_/delete_queue_ sizes seen by the last UpdateESDF        (:277) */
   int64_t voxels_changed;      /* voxels whose (distance, closest obstacle) record changed in the last UpdateESDF */
+  int64_t expansions;          /* EXACT mode: non-stale queue pops = the reference's "Expanding N nodes" (ESDFMap.cpp:394); FAST: 0 */
   int64_t voxels_reset;        /* dependants of deleted obstacles cleared by the last UpdateESDF (E2) */
   int64_t tile_visits;         /* 8^3 tile relaxations run by the last UpdateESDF */
   int64_t generations;         /* wavefront generations of the last UpdateESDF */
@@ -67,7 +78,7 @@ typedef struct fiesta_stats {
   float ms_update_esdf;        /* device time of the last UpdateESDF (whole call) */
   float ms_esdf_delete_scan;   /* ... of which: dense dependant scan (E2) */
   float ms_esdf_wavefront;     /* ... of which: tile wavefront kernel (E3) */
-  float reserved_f[3];
+  float reserved_f[1];
 } fiesta_stats;
 
 /* ---- lifetime: `new ESDFMap(...)` / `delete` (Fiesta.h:96,137) ---- */

@@ -29,7 +29,7 @@ def test_header_and_library_agree(lib):
 def test_struct_layouts_match_header():
     assert C.sizeof(fiesta_b200.Config) == 3 * 8 + 8 + 3 * 8 + 4 + 7 * 4
     assert C.sizeof(fiesta_b200.RaycastParams) == 16
-    assert C.sizeof(fiesta_b200.Stats) == 13 * 8 + 8 * 4
+    assert C.sizeof(fiesta_b200.Stats) == 14 * 8 + 6 * 4
 
 
 def test_sass_is_sm100a_with_tma():

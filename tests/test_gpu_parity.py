@@ -109,3 +109,81 @@ def test_raycast_counters_match_serial_reference(oracle_built):
         assert r["occ"] == 0, (f, r)
         print("frame", f, r, dev.stats())
         sc.step()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# FIESTA_MODE_EXACT: the device reproduces the reference's sequential FIFO order, so EVERYTHING is bit-exact:
+# distance_, closest_obstacle_ (no tie tolerance) and the number of non-stale queue pops ("Expanding N nodes").
+def make_exact_pair(oracle_built, origin, res, size, params):
+    import fiesta_b200
+    dev = fiesta_b200.ESDFMap(origin, res, size, mode="exact")
+    ora = oracle_built.OracleMap(origin, res, size)
+    dev.SetParameters(*params)
+    ora.SetParameters(*params)
+    return dev, ora
+
+
+def assert_identical(dev, ora, tag):
+    r = compare(dev, ora)
+    assert r["occ"] == 0 and r["dist"] == 0 and r["cobs_tie"] == 0 and r["cobs_nontie"] == 0, (tag, r)
+    sd, so = dev.stats(), ora.stats()
+    assert sd["expansions"] == so["expansions"], (tag, sd["expansions"], so["expansions"])
+    return r
+
+
+def test_exact_pillar_replay(oracle_built):
+    dev, ora = make_exact_pair(oracle_built, (-6.4, -6.4, 0.0), 0.2, (12.8, 12.8, 12.8), scenes.PARAMS_TOGGLE)
+    allv = scenes.all_voxels(dev.grid_size)
+    feed(dev, ora, allv, np.zeros(len(allv), np.uint8))
+    sites = scenes.pillar_sites()
+    rng = np.random.default_rng(1)
+    order = rng.permutation(len(sites))                       # shuffled variant
+    for k in order:
+        feed(dev, ora, scenes.pillar(*sites[k]), np.ones(25, np.uint8))
+        assert_identical(dev, ora, "pillar %d" % k)
+    for k in order[::-1][:13]:
+        feed(dev, ora, scenes.pillar(*sites[k]), np.zeros(25, np.uint8))
+        assert_identical(dev, ora, "delete %d" % k)
+
+
+@pytest.mark.parametrize("observed", [1.0, 0.6])
+def test_exact_random_insert_delete(oracle_built, observed):
+    """Mixed insert/delete rounds, fully and partially (salt-and-pepper) observed: the adversarial case for tie-breaks."""
+    rng = np.random.default_rng(21)
+    dev, ora = make_exact_pair(oracle_built, (-2.0, -2.0, -2.0), 0.1, (3.95, 3.95, 3.15), scenes.PARAMS_TOGGLE)
+    gs = dev.grid_size
+    allv = scenes.all_voxels(gs)
+    sel = allv[rng.random(len(allv)) < observed]
+    sel = sel[rng.permutation(len(sel))]                      # scrambled first-observation order
+    feed(dev, ora, sel, (rng.random(len(sel)) < 0.01).astype(np.uint8))
+    assert_identical(dev, ora, "observe")
+    for r in range(6):
+        n = 1500
+        vox = np.stack([rng.integers(0, gs[i], n) for i in range(3)], -1).astype(np.int32)
+        feed(dev, ora, vox, (rng.random(n) < 0.5).astype(np.uint8))
+        assert_identical(dev, ora, "round %d" % r)
+    pos = rng.uniform(-1.9, 1.0, (2000, 3))
+    d1, g1 = dev.GetDistWithGradTrilinearBatch(pos)
+    d2, g2 = ora.GetDistWithGradTrilinearBatch(pos)
+    assert np.array_equal(d1, d2) and np.array_equal(g1, g2)
+
+
+def test_exact_raycast_frames(oracle_built):
+    """Depth frames into a partially observed map: counters, occupancy, distance_, closest_obstacle_ and the expansion
+    count all equal the serial reference, frame after frame."""
+    dev, ora = make_exact_pair(oracle_built, (-6.4, -6.4, -3.2), 0.1, (12.8, 12.8, 6.4), scenes.PARAMS_DEFAULT)
+    sc = scenes.Scene((5.0, 5.0, 2.5), 20, 5, seed=2)
+    for f, (p, yaw) in enumerate(scenes.pose_walk(5, seed=3)):
+        pts, T = scenes.depth_frame(sc, p, yaw, width=160, height=120, scale=0.25)
+        assert dev.RaycastFrame(pts, T, 0.5, 5.0) == ora.RaycastFrame(pts, T, 0.5, 5.0)
+        (h1, t1), (h2, t2) = dev.export_counters(), ora.export_counters()
+        assert np.array_equal(h1, h2) and np.array_equal(t1, t2)
+        assert dev.UpdateOccupancy(True) == ora.UpdateOccupancy(True)
+        sd, so = dev.stats(), ora.stats()
+        dev.UpdateESDF()
+        ora.UpdateESDF()
+        sd, so = dev.stats(), ora.stats()
+        assert sd["inserts"] == so["inserts"] and sd["deletes"] == so["deletes"], (f, sd, so)
+        r = assert_identical(dev, ora, "frame %d" % f)
+        print("exact frame", f, r, {k: sd[k] for k in ("expansions", "voxels_changed", "generations", "ms_update_esdf")})
+        sc.step()
