@@ -187,3 +187,24 @@ def test_exact_raycast_frames(oracle_built):
         r = assert_identical(dev, ora, "frame %d" % f)
         print("exact frame", f, r, {k: sd[k] for k in ("expansions", "voxels_changed", "generations", "ms_update_esdf")})
         sc.step()
+
+
+def test_exact_256_insert_delete_replay(oracle_built):
+    """north_star: bit-exact closest-obstacle indices vs the reference on a 256^3 insert/delete replay (all voxels observed,
+    then +20 000 inserts / -10 000 deletes per frame)."""
+    rng = np.random.default_rng(6)
+    dev, ora = make_exact_pair(oracle_built, (-6.4, -6.4, -6.4), 0.05, (12.8, 12.8, 12.8), scenes.PARAMS_TOGGLE)
+    assert dev.grid_size == (256, 256, 256)
+    allv = scenes.all_voxels(dev.grid_size)
+    feed(dev, ora, allv, np.zeros(len(allv), np.uint8))
+    occupied = np.empty((0, 3), np.int32)
+    for f in range(2):
+        ins = rng.integers(0, 256, (20000, 3)).astype(np.int32)
+        dele = occupied[rng.permutation(len(occupied))[:10000]] if len(occupied) else np.empty((0, 3), np.int32)
+        vox = np.concatenate([ins, dele])
+        occ = np.concatenate([np.ones(len(ins), np.uint8), np.zeros(len(dele), np.uint8)])
+        perm = rng.permutation(len(vox))
+        feed(dev, ora, vox[perm], occ[perm])
+        r = assert_identical(dev, ora, "frame %d" % f)
+        print("256^3 frame", f, r, dev.stats()["expansions"], dev.stats()["ms_update_esdf"])
+        occupied = np.unique(np.concatenate([occupied, ins]), axis=0)
