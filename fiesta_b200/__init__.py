@@ -32,6 +32,10 @@ class RaycastParams(C.Structure):
     _fields_ = [("min_ray_length", C.c_double), ("max_ray_length", C.c_double)]
 
 
+class ShardInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("rank", "world", "x_begin", "x_end", "has_lo", "has_hi")] + [("layer_words", C.c_int64)]
+
+
 class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "occupancy_updates", "inserts", "deletes", "voxels_changed", "expansions", "voxels_reset", "tile_visits", "generations",
@@ -52,7 +56,7 @@ SYMBOLS = [
     "fiesta_get_distance_pos", "fiesta_get_distance_vox", "fiesta_get_occupancy_pos", "fiesta_get_occupancy_vox",
     "fiesta_get_dist_grad_trilinear", "fiesta_get_distance_batch_pos", "fiesta_get_dist_grad_trilinear_batch",
     "fiesta_export_distance", "fiesta_export_closest_obstacle", "fiesta_export_occupancy", "fiesta_export_counters",
-    "fiesta_get_stats", "fiesta_synchronize",
+    "fiesta_get_stats", "fiesta_synchronize", "fiesta_set_shard", "fiesta_shard_pack", "fiesta_shard_ingest", "fiesta_shard_relax",
 ]
 
 _lib = None
@@ -243,6 +247,25 @@ class ESDFMap:
         s = Stats()
         self._ck(self._L.fiesta_get_stats(self._h, C.byref(s)), "get_stats")
         return s.asdict()
+
+    # --- multi-GPU x-slab sharding (see fiesta_b200/shard.py for the exchange loop) ---
+    def set_shard(self, rank, world):
+        info = ShardInfo()
+        self._ck(self._L.fiesta_set_shard(self._h, int(rank), int(world), C.byref(info)), "set_shard")
+        return info
+
+    def shard_pack(self, d_lo_ptr, d_hi_ptr):
+        self._ck(self._L.fiesta_shard_pack(self._h, C.c_void_p(d_lo_ptr or 0), C.c_void_p(d_hi_ptr or 0)), "shard_pack")
+
+    def shard_ingest(self, d_from_lo_ptr, d_from_hi_ptr):
+        ch = C.c_int64(0)
+        self._ck(self._L.fiesta_shard_ingest(self._h, C.c_void_p(d_from_lo_ptr or 0), C.c_void_p(d_from_hi_ptr or 0), C.byref(ch)), "shard_ingest")
+        return int(ch.value)
+
+    def shard_relax(self):
+        ch = C.c_int64(0)
+        self._ck(self._L.fiesta_shard_relax(self._h, C.byref(ch)), "shard_relax")
+        return int(ch.value)
 
     def synchronize(self):
         self._ck(self._L.fiesta_synchronize(self._h), "synchronize")

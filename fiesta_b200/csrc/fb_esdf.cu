@@ -30,7 +30,9 @@ namespace cg = cooperative_groups;
 __device__ __forceinline__ unsigned ld_cg_u32(const unsigned *p) { return __ldcg(p); }
 
 // Queue tile t for the generation identified by `stamp` (dedupe through tile_flag).
-__device__ __forceinline__ void fb_activate(const FbEsdfArgs &a, unsigned t, unsigned stamp, int which, bool work = true) {
+// `tyz` = tiles per x column; tiles outside this map's x-slab belong to another rank and are never queued here.
+__device__ __forceinline__ void fb_activate(const FbEsdfArgs &a, unsigned t, unsigned stamp, int which, bool work = true, unsigned tyz = 0) {
+  if (tyz) { const int txc = (int)(t / tyz); if (txc < a.tile_x_lo || txc >= a.tile_x_hi) return; }
   if (work) a.nb_flag[t] = stamp;
   if (atomicExch(&a.tile_flag[t], stamp) != stamp) {
     unsigned slot = atomicAdd(&a.ctr->n_list[which], 1u);
@@ -52,7 +54,7 @@ __global__ void k_seed_inserts(FbGeom g, FbEsdfArgs a, const uint32_t *ins, unsi
   int tz0 = max(z - 2, 0) >> 3, tz1 = min(z + 2, g.gz - 1) >> 3;
   for (int tx = tx0; tx <= tx1; ++tx)
     for (int ty = ty0; ty <= ty1; ++ty)
-      for (int tz = tz0; tz <= tz1; ++tz) fb_activate(a, (unsigned)((tx * g.ty + ty) * g.tz + tz), stamp, 0);
+      for (int tz = tz0; tz <= tz1; ++tz) fb_activate(a, (unsigned)((tx * g.ty + ty) * g.tz + tz), stamp, 0, true, (unsigned)(g.ty * g.tz));
 }
 
 // ---------------------------------------------------------------- E2
@@ -78,7 +80,7 @@ __global__ void k_delete_scan(FbGeom g, FbEsdfArgs a) {
       reinterpret_cast<uint4 *>(a.cobs)[v] = make_uint4(c[0], c[1], c[2], c[3]);
       long long ii = v << 2;                                // the 4 voxels share (x, y) and lie in at most 1 tile (z % 4 == 0)
       int z = (int)(ii % g.pz), y = (int)((ii / g.pz) % g.gy), x = (int)(ii / ((long long)g.pz * g.gy));
-      fb_activate(a, (unsigned)(((x >> 3) * g.ty + (y >> 3)) * g.tz + (z >> 3)), stamp, 0);
+      fb_activate(a, (unsigned)(((x >> 3) * g.ty + (y >> 3)) * g.tz + (z >> 3)), stamp, 0, true, (unsigned)(g.ty * g.tz));
     }
   }
   if (local_reset) atomicAdd(&a.ctr->voxels_reset, (unsigned long long)local_reset);
@@ -370,7 +372,7 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
           if (oz < 0) need = need && (mnz < 2); if (oz > 0) need = need && (mxz > 5);
           const int nx = txc + ox, ny = tyc + oy, nzc = tzc + oz;
           if (need && nx >= 0 && nx < g.tx && ny >= 0 && ny < g.ty && nzc >= 0 && nzc < g.tz)
-            fb_activate(a, (unsigned)((nx * g.ty + ny) * g.tz + nzc), stamp, (int)(cur ^ 1u));
+            fb_activate(a, (unsigned)((nx * g.ty + ny) * g.tz + nzc), stamp, (int)(cur ^ 1u), true, (unsigned)(g.ty * g.tz));
         }
       }
     }
@@ -386,6 +388,47 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
     if (my_visits) atomicAdd(&a.ctr->tile_visits, my_visits);
     if (blockIdx.x == 0) { a.ctr->generations = gen; a.ctr->gen_stamp = stamp0 + gen + 1u; }
   }
+}
+
+// ---------------------------------------------------------------- x-slab sharding: ghost layers
+// Received ghost layers (2 x-layers below and above the slab, as sent by the neighbouring ranks) are compared with the local
+// copy; a voxel whose record differs is overwritten, marked FRESH (it pushes into this slab in the next generation) and the
+// own tiles within reach are queued.
+__global__ void k_halo_ingest(FbGeom g, FbEsdfArgs a, const uint32_t *recv, int x_first, int nlayers, int own_tile_x, unsigned *nchanged) {
+  const long long per = (long long)g.gy * g.pz;
+  const unsigned stamp = a.ctr->gen_stamp;
+  unsigned local = 0;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < per * nlayers; k += (long long)gridDim.x * blockDim.x) {
+    const int x = x_first + (int)(k / per);
+    const long long r = k % per;
+    const int y = (int)(r / g.pz), z = (int)(r % g.pz);
+    if (z >= g.gz) continue;
+    const long long ii = fb_ii(g, x, y, z);
+    const uint32_t nw = recv[k] & FB_CODE_MASK, old = a.cobs[ii] & FB_CODE_MASK;
+    if (nw != old) {
+      a.cobs[ii] = nw | FB_FRESH;
+      ++local;
+      const int ty0 = max(y - 2, 0) >> 3, ty1 = min(y + 2, g.gy - 1) >> 3, tz0 = max(z - 2, 0) >> 3, tz1 = min(z + 2, g.gz - 1) >> 3;
+      for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tz = tz0; tz <= tz1; ++tz) fb_activate(a, (unsigned)((own_tile_x * g.ty + ty) * g.tz + tz), stamp, 0, true, (unsigned)(g.ty * g.tz));
+    }
+  }
+  if (local) atomicAdd(nchanged, local);
+}
+__global__ void k_halo_retire(FbGeom g, uint32_t *cobs, int x_first, int nlayers) {
+  const long long per = (long long)g.gy * g.pz;
+  uint32_t *p = cobs + (long long)x_first * per;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < per * nlayers; k += (long long)gridDim.x * blockDim.x) p[k] &= FB_CODE_MASK;
+}
+cudaError_t fb_esdf_halo_ingest(const FbGeom &g, const FbEsdfArgs &a, const uint32_t *recv, int x_first, int nlayers, int own_tile_x, unsigned *d_nchanged, cudaStream_t s) {
+  if (nlayers <= 0) return cudaSuccess;
+  k_halo_ingest<<<148 * 4, 256, 0, s>>>(g, a, recv, x_first, nlayers, own_tile_x, d_nchanged);
+  return cudaGetLastError();
+}
+cudaError_t fb_esdf_halo_retire(const FbGeom &g, uint32_t *cobs, int x_first, int nlayers, cudaStream_t s) {
+  if (nlayers <= 0) return cudaSuccess;
+  k_halo_retire<<<148 * 4, 256, 0, s>>>(g, cobs, x_first, nlayers);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------- host side

@@ -60,6 +60,8 @@ struct fiesta_map {
   cudaEvent_t ev[4];
   unsigned long long *d_dbg;
   int mode;
+  int shard_rank, shard_world, tile_x_lo, tile_x_hi;
+  unsigned *d_halo_changed;
   FbExact X;
   unsigned n_xtouched;
   fiesta_stats st;
@@ -308,6 +310,7 @@ void fiesta_destroy(fiesta_map *m) {
   for (void *p : dev) if (p) cudaFree(p);
   if (m->mode == FIESTA_MODE_EXACT) fb_exact_free(&m->X);
   if (m->d_dbg) cudaFree(m->d_dbg);
+  if (m->d_halo_changed) cudaFree(m->d_halo_changed);
   if (m->h_ctr) cudaFreeHost(m->h_ctr);
   if (m->h_ev) cudaFreeHost(m->h_ev);
   for (int i = 0; i < 4; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
@@ -332,6 +335,7 @@ int fiesta_create(const fiesta_config *cfg, fiesta_map **out) {
   memset((void *)m, 0, sizeof(*m));
   m->device = cfg->device;
   m->mode = cfg->mode == FIESTA_MODE_EXACT ? FIESTA_MODE_EXACT : FIESTA_MODE_FAST;
+  m->shard_rank = 0; m->shard_world = 1;
   FbGeom &g = m->g;
   int gs[3];
   for (int i = 0; i < 3; ++i) {                                           // ctor, ESDFMap.cpp:171-186
@@ -356,6 +360,7 @@ int fiesta_create(const fiesta_config *cfg, fiesta_map **out) {
   for (int i = 0; i < 3; ++i) { g.min_vec[i] = g.last_min_vec[i] = 0; }   // SetOriginalRange, ESDFMap.cpp:819-822
   g.max_vec[0] = g.last_max_vec[0] = g.gx - 1; g.max_vec[1] = g.last_max_vec[1] = g.gy - 1; g.max_vec[2] = g.last_max_vec[2] = g.gz - 1;
   set_box_flag(g);
+  m->tile_x_lo = 0; m->tile_x_hi = g.tx;
 
 #define CKD(call)                                                                        \
   do {                                                                                   \
@@ -626,6 +631,7 @@ int fiesta_update_esdf(fiesta_map *m) {
   a.cobs = m->cobs; a.cobs_b = m->cobs_b; a.occ = m->occ; a.occbits = m->occbits; a.tile_flag = m->tile_flag; a.nb_flag = m->nb_flag;
   for (int k = 0; k < 2; ++k) { a.list[k] = m->list[k]; a.changed[k] = m->changed[k]; a.changed_bbox[k] = m->changed_bbox[k]; }
   a.ctr = m->d_ctr; a.l_occ = m->l_occ;
+  a.tile_x_lo = m->tile_x_lo; a.tile_x_hi = m->tile_x_hi;
   a.dbg = nullptr;
   static const bool dbg_wf = getenv("FIESTA_DEBUG_WF") != nullptr;
   if (dbg_wf) { if (!m->d_dbg) CK(cudaMalloc((void **)&m->d_dbg, 1024 * 8)); CK(cudaMemsetAsync(m->d_dbg, 0, 1024 * 8, m->stream)); a.dbg = m->d_dbg; }
@@ -778,6 +784,69 @@ int fiesta_export_counters(fiesta_map *m, int *hit, int *tot) {
   int r = flush_events(m);
   if (r) return r;
   return run_export(m, nullptr, nullptr, nullptr, hit, tot);
+}
+
+// ---- x-slab sharding
+static void fill_esdf_args(fiesta_map *m, FbEsdfArgs &a) {
+  a.cobs = m->cobs; a.cobs_b = m->cobs_b; a.occ = m->occ; a.occbits = m->occbits; a.tile_flag = m->tile_flag; a.nb_flag = m->nb_flag;
+  for (int k = 0; k < 2; ++k) { a.list[k] = m->list[k]; a.changed[k] = m->changed[k]; a.changed_bbox[k] = m->changed_bbox[k]; }
+  a.ctr = m->d_ctr; a.l_occ = m->l_occ; a.tile_x_lo = m->tile_x_lo; a.tile_x_hi = m->tile_x_hi; a.dbg = nullptr;
+}
+int fiesta_set_shard(fiesta_map *m, int rank, int world, fiesta_shard_info *out) {
+  if (!m || world < 1 || rank < 0 || rank >= world) { set_error("fiesta_set_shard: bad rank/world"); return FIESTA_ERR_INVALID; }
+  if (m->mode != FIESTA_MODE_FAST) { set_error("fiesta_set_shard: sharding is implemented for FIESTA_MODE_FAST only"); return FIESTA_ERR_INVALID; }
+  if (world > m->g.tx) { set_error("fiesta_set_shard: more ranks than 8-voxel tile columns"); return FIESTA_ERR_LIMIT; }
+  m->shard_rank = rank; m->shard_world = world;
+  m->tile_x_lo = (int)((long long)m->g.tx * rank / world);
+  m->tile_x_hi = (int)((long long)m->g.tx * (rank + 1) / world);
+  if (!m->d_halo_changed) CK(cudaMalloc((void **)&m->d_halo_changed, 16));
+  if (out) {
+    out->rank = rank; out->world = world;
+    out->x_begin = m->tile_x_lo * 8; out->x_end = m->tile_x_hi * 8 < m->g.gx ? m->tile_x_hi * 8 : m->g.gx;
+    out->has_lo = rank > 0; out->has_hi = rank + 1 < world;
+    out->layer_words = 2ll * m->g.gy * m->g.pz;
+  }
+  return FIESTA_OK;
+}
+int fiesta_shard_pack(fiesta_map *m, uint32_t *d_lo, uint32_t *d_hi) {
+  if (!m) return FIESTA_ERR_INVALID;
+  CK(cudaSetDevice(m->device));
+  const long long per = (long long)m->g.gy * m->g.pz;
+  const int x0 = m->tile_x_lo * 8, x1 = m->tile_x_hi * 8 < m->g.gx ? m->tile_x_hi * 8 : m->g.gx;
+  if (d_lo && m->shard_rank > 0) CK(cudaMemcpyAsync(d_lo, m->cobs + (long long)x0 * per, 2 * per * 4, cudaMemcpyDeviceToDevice, m->stream));
+  if (d_hi && m->shard_rank + 1 < m->shard_world) CK(cudaMemcpyAsync(d_hi, m->cobs + (long long)(x1 - 2) * per, 2 * per * 4, cudaMemcpyDeviceToDevice, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return FIESTA_OK;
+}
+int fiesta_shard_ingest(fiesta_map *m, const uint32_t *d_from_lo, const uint32_t *d_from_hi, int64_t *changed) {
+  if (!m || !changed) return FIESTA_ERR_INVALID;
+  CK(cudaSetDevice(m->device));
+  FbEsdfArgs a; fill_esdf_args(m, a);
+  const int x0 = m->tile_x_lo * 8, x1 = m->tile_x_hi * 8 < m->g.gx ? m->tile_x_hi * 8 : m->g.gx;
+  CK(cudaMemsetAsync(m->d_halo_changed, 0, 4, m->stream));
+  if (d_from_lo && m->shard_rank > 0) { CK(fb_esdf_halo_ingest(m->g, a, d_from_lo, x0 - 2, 2, m->tile_x_lo, m->d_halo_changed, m->stream)); m->st.kernel_launches++; }
+  if (d_from_hi && m->shard_rank + 1 < m->shard_world) { CK(fb_esdf_halo_ingest(m->g, a, d_from_hi, x1, 2, m->tile_x_hi - 1, m->d_halo_changed, m->stream)); m->st.kernel_launches++; }
+  unsigned h = 0;
+  CK(cudaMemcpyAsync(&h, m->d_halo_changed, 4, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  *changed = h;
+  return FIESTA_OK;
+}
+int fiesta_shard_relax(fiesta_map *m, int64_t *changed) {
+  if (!m || !changed) return FIESTA_ERR_INVALID;
+  CK(cudaSetDevice(m->device));
+  FbEsdfArgs a; fill_esdf_args(m, a);
+  k_reset_esdf_ctr<<<1, 1, 0, m->stream>>>(m->d_ctr);
+  CK(fb_esdf_wavefront(m->g, a, m->tmap, m->wf_blocks, m->stream));
+  const int x0 = m->tile_x_lo * 8, x1 = m->tile_x_hi * 8 < m->g.gx ? m->tile_x_hi * 8 : m->g.gx;
+  if (m->shard_rank > 0) CK(fb_esdf_halo_retire(m->g, m->cobs, x0 - 2, 2, m->stream));
+  if (m->shard_rank + 1 < m->shard_world) CK(fb_esdf_halo_retire(m->g, m->cobs, x1, 2, m->stream));
+  m->st.kernel_launches += 4;
+  int r;
+  if ((r = fetch_counters(m))) return r;
+  *changed = (int64_t)m->h_ctr->voxels_changed;
+  m->st.voxels_changed += *changed; m->st.generations += m->h_ctr->generations; m->st.tile_visits += (int64_t)m->h_ctr->tile_visits;
+  return FIESTA_OK;
 }
 
 int fiesta_get_stats(fiesta_map *m, fiesta_stats *out) {

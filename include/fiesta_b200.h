@@ -142,6 +142,27 @@ int fiesta_export_closest_obstacle(fiesta_map *m, int *out_xyz);    /* closest_o
 int fiesta_export_occupancy(fiesta_map *m, double *out);            /* occupancy_buffer_ log-odds */
 int fiesta_export_counters(fiesta_map *m, int *num_hit, int *num_total); /* num_hit_, num_miss_ (all observations) */
 
+/* ---- multi-GPU: x-slab sharding of UpdateESDF (one process per GPU; the caller moves the ghost layers, e.g. with NCCL) ----
+ * Every rank holds the whole grid and integrates every frame identically (ray casting and UpdateOccupancy are replicated),
+ * but relaxes only the tile columns of its own x-slab.  dirs_ reaches 2 voxels (parameters.h:66-68), so the ghost layer is 2
+ * x-layers on each internal face; one x-layer is Gy*Pz contiguous records, so layers are sent as they lie in memory.
+ * Protocol per UpdateESDF:  fiesta_update_esdf();  repeat { fiesta_shard_pack -> exchange with rank-1 / rank+1 ->
+ * fiesta_shard_ingest -> fiesta_shard_relax; all-reduce the number of changed records } until it is 0 on every rank. */
+typedef struct fiesta_shard_info {
+  int32_t rank, world;
+  int32_t x_begin, x_end;        /* voxel x range owned by this rank */
+  int32_t has_lo, has_hi;        /* neighbours rank-1 / rank+1 exist */
+  int64_t layer_words;           /* 32-bit words in one ghost exchange buffer = 2 * Gy * Pz */
+} fiesta_shard_info;
+int fiesta_set_shard(fiesta_map *m, int rank, int world, fiesta_shard_info *out);
+/* Copy this rank's two lowest / two highest owned x-layers into the DEVICE buffers d_lo / d_hi (layer_words words each). */
+int fiesta_shard_pack(fiesta_map *m, uint32_t *d_lo, uint32_t *d_hi);
+/* Take the neighbours' boundary layers (DEVICE buffers; nullable where no neighbour exists): d_from_lo = rank-1's highest
+ * two layers, d_from_hi = rank+1's lowest two.  *changed = number of ghost records that differed. */
+int fiesta_shard_ingest(fiesta_map *m, const uint32_t *d_from_lo, const uint32_t *d_from_hi, int64_t *changed);
+/* Relax the slab again from the queued tiles; *changed = records changed inside the slab. */
+int fiesta_shard_relax(fiesta_map *m, int64_t *changed);
+
 int fiesta_get_stats(fiesta_map *m, fiesta_stats *out);
 /* Block until all work queued on the map's stream has finished. */
 int fiesta_synchronize(fiesta_map *m);
