@@ -1,0 +1,108 @@
+"""GPU edge cases the reference's own call sites exercise: empty / NaN / gated clouds, points outside the map, sentinel
+returns of the per-call API, and a local update box (SetUpdateRange)."""
+import numpy as np
+import pytest
+
+from tests import scenes
+from tests.parity import compare
+
+pytestmark = pytest.mark.gpu
+
+
+def pair(oracle_built, mode, origin=(-3.2, -3.2, -1.6), res=0.1, size=(6.4, 6.4, 3.2), params=scenes.PARAMS_DEFAULT):
+    import fiesta_b200
+    dev = fiesta_b200.ESDFMap(origin, res, size, mode=mode)
+    ora = oracle_built.OracleMap(origin, res, size)
+    dev.SetParameters(*params)
+    ora.SetParameters(*params)
+    return dev, ora
+
+
+def same_counters(dev, ora):
+    (h1, t1), (h2, t2) = dev.export_counters(), ora.export_counters()
+    return np.array_equal(h1, h2) and np.array_equal(t1, t2)
+
+
+@pytest.mark.parametrize("mode", ["fast", "exact"])
+def test_degenerate_clouds(oracle_built, mode):
+    dev, ora = pair(oracle_built, mode)
+    T = scenes.body_transform((0.013, -0.021, 0.009), 0.3)
+    rng = np.random.default_rng(0)
+    clouds = [
+        np.empty((0, 3), np.float32),                                            # empty frame
+        np.full((100, 3), np.nan, np.float32),                                   # all NaN (Fiesta.h:202)
+        (rng.normal(size=(500, 3)) * 0.1).astype(np.float32),                    # all shorter than min_ray_length (:209)
+        (rng.normal(size=(2000, 3)) * 20).astype(np.float32),                    # mostly far outside the map / clipped (:211-213)
+        np.tile(np.array([[1.0, 0.5, 0.2]], np.float32), (300, 1)),              # 300 identical points: endpoint dedupe (:227-230)
+        (rng.normal(size=(3000, 3)) * 1.5).astype(np.float32),
+    ]
+    for k, pts in enumerate(clouds):
+        assert dev.RaycastFrame(pts, T, 0.5, 5.0) == ora.RaycastFrame(pts, T, 0.5, 5.0), k
+        assert same_counters(dev, ora), k
+        assert dev.CheckUpdate() == ora.CheckUpdate(), k
+        if dev.CheckUpdate():
+            assert dev.UpdateOccupancy(True) == ora.UpdateOccupancy(True)
+            dev.UpdateESDF(); ora.UpdateESDF()
+        r = compare(dev, ora)
+        assert r["occ"] == 0, (k, r)
+        if mode == "exact":
+            assert r["dist"] == 0 and r["cobs_tie"] == 0 and r["cobs_nontie"] == 0, (k, r)
+    assert dev.stats()["rays_dropped"] == ora.hung_rays()
+
+
+def test_per_call_api_and_sentinels(oracle_built):
+    """int SetOccupancy(pos|vox, occ) return values and queries (ESDFMap.cpp:401-437, 452-540), call by call."""
+    dev, ora = pair(oracle_built, "exact", params=scenes.PARAMS_TOGGLE)
+    rng = np.random.default_rng(1)
+    for _ in range(3000):
+        p = rng.uniform(-3.6, 3.6, 3) * (1, 1, 0.55)
+        occ = int(rng.integers(0, 3))                                            # 2 is invalid -> -10000
+        assert dev.SetOccupancy(tuple(p), occ) == ora.SetOccupancy(tuple(p), occ)
+    for _ in range(500):
+        v = tuple(int(x) for x in rng.integers(0, 32, 3))
+        occ = int(rng.integers(0, 2))
+        assert dev.SetOccupancy(v, occ) == ora.SetOccupancy(v, occ)
+    edge = (3.2, 3.2, 1.6)                                                       # exactly on the upper face: in map, voxel index aliases
+    assert dev.SetOccupancy(edge, 1) == ora.SetOccupancy(edge, 1)
+    assert same_counters(dev, ora)
+    assert dev.UpdateOccupancy(True) == ora.UpdateOccupancy(True)
+    dev.UpdateESDF(); ora.UpdateESDF()
+    r = compare(dev, ora)
+    assert r["dist"] == 0 and r["cobs_tie"] == 0 and r["occ"] == 0, r
+    for _ in range(300):
+        p = tuple(rng.uniform(-3.6, 3.6, 3) * (1, 1, 0.55))
+        assert dev.GetDistance(p) == ora.GetDistance(p)
+        assert dev.GetOccupancy(p) == ora.GetOccupancy(p)
+        d1, g1 = dev.GetDistWithGradTrilinear(p)
+        d2, g2 = ora.GetDistWithGradTrilinear(p)
+        inside = all(-3.1 < p[i] < (3.0, 3.0, 1.4)[i] for i in range(3))
+        if inside or d2 == -1:
+            assert d1 == d2 and np.array_equal(g1, g2), p
+    v = (5, 6, 7)
+    assert dev.GetDistance(v) == ora.GetDistance(v) and dev.GetOccupancy(v) == ora.GetOccupancy(v)
+
+
+@pytest.mark.parametrize("mode", ["fast", "exact"])
+def test_local_update_box(oracle_built, mode):
+    """SetUpdateRange (ESDFMap.cpp:792-810): observations outside the box are not counted and the wave stays inside it."""
+    dev, ora = pair(oracle_built, mode, params=scenes.PARAMS_TOGGLE)
+    allv = scenes.all_voxels(dev.grid_size)
+    for m in (dev, ora):
+        m.SetOccupancyBatchVox(allv, np.zeros(len(allv), np.uint8)); m.UpdateOccupancy(True); m.UpdateESDF()
+    rng = np.random.default_rng(2)
+    lo, hi = (-1.5, -1.0, -0.8), (1.2, 1.9, 0.9)
+    for r in range(3):
+        for m in (dev, ora):
+            m.SetUpdateRange(lo, hi)
+        vox = np.stack([rng.integers(0, dev.grid_size[i], 1500) for i in range(3)], -1).astype(np.int32)
+        occ = (rng.random(1500) < 0.5).astype(np.uint8)
+        assert np.array_equal(dev.SetOccupancyBatchVox(vox, occ), ora.SetOccupancyBatchVox(vox, occ))
+        assert same_counters(dev, ora)
+        assert dev.UpdateOccupancy(True) == ora.UpdateOccupancy(True)
+        dev.UpdateESDF(); ora.UpdateESDF()
+        res = compare(dev, ora)
+        assert res["occ"] == 0 and res["dist"] == 0 and res["cobs_nontie"] == 0, (r, res)
+        if mode == "exact":
+            assert res["cobs_tie"] == 0, (r, res)
+    for m in (dev, ora):
+        m.SetOriginalRange()
