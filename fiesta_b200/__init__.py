@@ -56,7 +56,7 @@ SYMBOLS = [
     "fiesta_get_distance_pos", "fiesta_get_distance_vox", "fiesta_get_occupancy_pos", "fiesta_get_occupancy_vox",
     "fiesta_get_dist_grad_trilinear", "fiesta_get_distance_batch_pos", "fiesta_get_dist_grad_trilinear_batch",
     "fiesta_export_distance", "fiesta_export_closest_obstacle", "fiesta_export_occupancy", "fiesta_export_counters",
-    "fiesta_get_stats", "fiesta_synchronize", "fiesta_set_shard", "fiesta_shard_pack", "fiesta_shard_ingest", "fiesta_shard_relax",
+    "fiesta_get_stats", "fiesta_synchronize", "fiesta_set_shard", "fiesta_shard_pack", "fiesta_shard_ingest", "fiesta_shard_relax", "fiesta_get_point_cloud", "fiesta_get_slice_marker",
 ]
 
 _lib = None
@@ -266,6 +266,23 @@ class ESDFMap:
         ch = C.c_int64(0)
         self._ck(self._L.fiesta_shard_relax(self._h, C.byref(ch)), "shard_relax")
         return int(ch.value)
+
+    # --- visualisation extraction (ESDFMap.h:144-145) ---
+    def GetPointCloud(self, vis_lower_bound, vis_upper_bound):
+        n = C.c_int64(0)
+        self._ck(self._L.fiesta_get_point_cloud(self._h, int(vis_lower_bound), int(vis_upper_bound), None, C.c_int64(0), C.byref(n)), "GetPointCloud")
+        out = np.empty((n.value, 3), np.float32)
+        if n.value:
+            self._ck(self._L.fiesta_get_point_cloud(self._h, int(vis_lower_bound), int(vis_upper_bound), out.ctypes, n, C.byref(n)), "GetPointCloud")
+        return out
+
+    def GetSliceMarker(self, slice_, max_dist):
+        n = C.c_int64(0)
+        self._ck(self._L.fiesta_get_slice_marker(self._h, int(slice_), C.c_double(max_dist), None, None, C.c_int64(0), C.byref(n)), "GetSliceMarker")
+        xyz, rgba = np.empty((n.value, 3), np.float64), np.empty((n.value, 4), np.float32)
+        if n.value:
+            self._ck(self._L.fiesta_get_slice_marker(self._h, int(slice_), C.c_double(max_dist), xyz.ctypes, rgba.ctypes, n, C.byref(n)), "GetSliceMarker")
+        return xyz, rgba
 
     def synchronize(self):
         self._ck(self._L.fiesta_synchronize(self._h), "synchronize")

@@ -225,13 +225,19 @@ __global__ void k_x_init_beh(const uint32_t *E, unsigned n, const uint32_t *cobs
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) B[i] = (X_PUSH << 32) | (cobs[E[i]] & FB_CODE_MASK);
 }
-__global__ void k_x_eval(FbGeom g, const uint32_t *E, unsigned n, const uint32_t *cobs, const uint32_t *M, const unsigned long long *Bin,
-                         unsigned long long *Bout, unsigned *changed) {
+// One round of the behaviour fixpoint.  B is updated IN PLACE (elements evaluated later in the same round already see the
+// new behaviour of earlier ones); an element is re-evaluated only in the first round of a generation or when an element
+// within reach (<= 4 voxels: its own 8^3 tile or one of the 26 around it) changed its behaviour in the previous round.
+// The loop ends with a round in which nothing changed, which reads a stable B: that state is the sequential execution.
+__global__ void k_x_eval(FbGeom g, const uint32_t *E, unsigned n, const uint32_t *cobs, const uint32_t *M, unsigned long long *B,
+                         uint32_t *tdirty, unsigned stamp, int first_round, unsigned *changed) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int x, y, z; x_coords(g, E[i], x, y, z);
+  const int tx = x >> 3, ty = y >> 3, tz = z >> 3;
+  if (!first_round && tdirty[(tx * g.ty + ty) * g.tz + tz] != stamp) return;
   const unsigned T0 = i * 32u;
-  const XState s = x_state(g, cobs, M, Bin, x, y, z, T0);
+  const XState s = x_state(g, cobs, M, B, x, y, z, T0);
   const uint32_t c0 = cobs[E[i]] & FB_CODE_MASK;
   unsigned long long nb;
   if (s.d != x_dist_of(x, y, z, c0)) nb = X_DEAD << 32;       // `xx.distance_ != distance_buffer_[idx]`: stale (:345)
@@ -240,15 +246,20 @@ __global__ void k_x_eval(FbGeom g, const uint32_t *E, unsigned n, const uint32_t
     for (int k = 0; k < 24; ++k) {                             // pull phase (:349-367)
       const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
       if (!fb_in_range(g, nx, ny, nz) || !fb_in_grid(g, nx, ny, nz)) continue;
-      const XState sn = x_state(g, cobs, M, Bin, nx, ny, nz, T0);
+      const XState sn = x_state(g, cobs, M, B, nx, ny, nz, T0);
       if (sn.c < 2u) continue;
       const unsigned t = x_d2(x, y, z, sn.c);
       if (curd > t) { curd = t; curc = sn.c; ch = true; }
     }
     nb = ch ? ((X_PULL << 32) | curc) : ((X_PUSH << 32) | s.c);
   }
-  Bout[i] = nb;
-  if (nb != Bin[i]) *changed = 1u;
+  if (nb != B[i]) {
+    B[i] = nb;
+    *changed = 1u;
+    for (int a = max(tx - 1, 0); a <= min(tx + 1, g.tx - 1); ++a)
+      for (int b = max(ty - 1, 0); b <= min(ty + 1, g.ty - 1); ++b)
+        for (int c = max(tz - 1, 0); c <= min(tz + 1, g.tz - 1); ++c) tdirty[(a * g.ty + b) * g.tz + c] = stamp + 1u;
+  }
 }
 // Final writes of the generation -> slots (timestamp order) of the next generation's queue.
 __global__ void k_x_commit(FbGeom g, const uint32_t *E, unsigned n, const uint32_t *cobs, const uint32_t *M, const unsigned long long *B,
@@ -349,17 +360,18 @@ cudaError_t fb_exact_init(FbExact *X, const FbGeom &g, cudaStream_t s) {
   const size_t P = (size_t)g.ptotal;
   XCK(cudaMalloc((void **)&X->M, P * 4)); XCK(cudaMalloc((void **)&X->LS, P * 8)); XCK(cudaMalloc((void **)&X->tkey, P * 8));
   XCK(cudaMalloc((void **)&X->touched, P * 4));
+  XCK(cudaMalloc((void **)&X->tdirty, (size_t)g.ntiles * 4)); XCK(cudaMemsetAsync(X->tdirty, 0, (size_t)g.ntiles * 4, s));
   XCK(cudaMalloc((void **)&X->d_count, 16)); XCK(cudaMalloc((void **)&X->d_flag, 16));
   XCK(cudaMallocHost((void **)&X->h_count, 16));
   XCK(cudaMemsetAsync(X->d_count, 0, 16, s)); XCK(cudaMemsetAsync(X->d_flag, 0, 16, s));
   k_x_fill32<<<148 * 8, 256, 0, s>>>(X->M, P, XNONE);
   k_x_fill64<<<148 * 8, 256, 0, s>>>(X->tkey, P, ~0ull);
   XCK(cudaMemsetAsync(X->LS, 0, P * 8, s));
-  X->tclock = 1; X->key_base = 0;
+  X->tclock = 1; X->key_base = 0; X->eval_clock = 1;
   return cudaGetLastError();
 }
 void fb_exact_free(FbExact *X) {
-  void *p[] = {X->M, X->LS, X->tkey, X->touched, X->d_count, X->d_flag, X->E[0], X->E[1], X->B[0], X->B[1], X->slotv, X->slotc, X->slotf, X->sel,
+  void *p[] = {X->M, X->LS, X->tkey, X->touched, X->tdirty, X->d_count, X->d_flag, X->E[0], X->E[1], X->B[0], X->B[1], X->slotv, X->slotc, X->slotf, X->sel,
                X->k1, X->k2, X->k1b, X->k2b, X->dv, X->idx[0], X->idx[1], X->deps, X->nc[0], X->nc[1], X->flags, X->flags2, X->cub_tmp};
   for (void *q : p) if (q) cudaFree(q);
   if (X->h_count) cudaFreeHost(X->h_count);
@@ -505,11 +517,11 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
     if ((e = x_ensure(X, &X->slotf, &X->cap_slotf, nslots))) return e;
     if ((e = x_ensure(X, &X->sel, &X->cap_sel, nslots))) return e;
     k_x_init_beh<<<nblk(nE), 256, 0, s>>>(X->E[cur], nE, cobs, X->B[0]);
-    int b = 0;
+    const int b = 0;
     for (int it = 0; it < 100000; ++it) {
-      k_x_eval<<<nblk(nE, 128), 128, 0, s>>>(g, X->E[cur], nE, cobs, X->M, X->B[b], X->B[b ^ 1], X->d_flag);
+      ++X->eval_clock;
+      k_x_eval<<<nblk(nE, 128), 128, 0, s>>>(g, X->E[cur], nE, cobs, X->M, X->B[0], X->tdirty, X->eval_clock, it == 0, X->d_flag);
       *launches += 1;
-      b ^= 1;
       unsigned ch = 0;
       if ((e = x_flag(X, s, &ch))) return e;
       st->eval_rounds++;

@@ -16,6 +16,8 @@ struct FbExact {
   unsigned long long tclock;   // relink clock
   unsigned long long key_base; // observation clock
   unsigned *d_count, *d_flag, *h_count;
+  uint32_t *tdirty;            // per 8^3 tile: evaluation round in which its elements must be re-evaluated
+  unsigned eval_clock;
   uint32_t *E[2]; size_t cap_E[2];
   unsigned long long *B[2]; size_t cap_B[2];
   uint32_t *slotv, *slotc, *sel; uint8_t *slotf; size_t cap_slotv, cap_slotc, cap_sel, cap_slotf;

@@ -849,6 +849,25 @@ int fiesta_shard_relax(fiesta_map *m, int64_t *changed) {
   return FIESTA_OK;
 }
 
+int fiesta_get_point_cloud(fiesta_map *m, int lo, int hi, float *out, int64_t cap, int64_t *count) {
+  if (!m || !count || (cap > 0 && !out)) return FIESTA_ERR_INVALID;
+  CK(cudaSetDevice(m->device));
+  long long c = 0;
+  CK(fb_vis_point_cloud(m->g, m->occ, m->l_occ, lo, hi, out, cap, &c, m->stream));
+  m->st.kernel_launches += 3;
+  *count = c;
+  return FIESTA_OK;
+}
+int fiesta_get_slice_marker(fiesta_map *m, int slice, double max_dist, double *xyz, float *rgba, int64_t cap, int64_t *count) {
+  if (!m || !count || (cap > 0 && (!xyz || !rgba))) return FIESTA_ERR_INVALID;
+  CK(cudaSetDevice(m->device));
+  long long c = 0;
+  CK(fb_vis_slice(m->g, m->cobs, slice, max_dist, xyz, rgba, cap, &c, m->stream));
+  m->st.kernel_launches += 3;
+  *count = c;
+  return FIESTA_OK;
+}
+
 int fiesta_get_stats(fiesta_map *m, fiesta_stats *out) {
   if (!m || !out) return FIESTA_ERR_INVALID;
   *out = m->st;

@@ -163,6 +163,14 @@ int fiesta_shard_ingest(fiesta_map *m, const uint32_t *d_from_lo, const uint32_t
 /* Relax the slab again from the queued tiles; *changed = records changed inside the slab. */
 int fiesta_shard_relax(fiesta_map *m, int64_t *changed);
 
+/* ---- visualisation extraction on the device (the step right after the path) ----
+ * ESDFMap::GetPointCloud (ESDFMap.cpp:544-582): centres (3 floats each, geometry_msgs::Point32) of the occupied voxels inside the
+ * update box with vis_lower <= z index <= vis_upper, in the reference's loop order.  *count = number found (may exceed cap). */
+int fiesta_get_point_cloud(fiesta_map *m, int vis_lower_bound, int vis_upper_bound, float *out_xyz, int64_t cap, int64_t *count);
+/* ESDFMap::GetSliceMarker (ESDFMap.cpp:639-699): points (3 doubles) and RainbowColorMap colours (4 floats rgba) of the voxels of
+ * z-slice `slice` inside the update box whose distance is in [0, +10000). */
+int fiesta_get_slice_marker(fiesta_map *m, int slice, double max_dist, double *out_xyz, float *out_rgba, int64_t cap, int64_t *count);
+
 int fiesta_get_stats(fiesta_map *m, fiesta_stats *out);
 /* Block until all work queued on the map's stream has finished. */
 int fiesta_synchronize(fiesta_map *m);

@@ -36,8 +36,7 @@ class ESDFMap {
   fiesta_map *h_ = nullptr;
   double resolution_;
   Eigen::Vector3d origin_;
-  Eigen::Vector3i grid_size_, min_vec_, max_vec_;
-  double min_occupancy_log_ = 0;
+  Eigen::Vector3i grid_size_;
 
   static void check(int rc, const char *what) {
     if (rc != FIESTA_OK) throw std::runtime_error(std::string(what) + ": " + fiesta_last_error());
@@ -61,8 +60,6 @@ class ESDFMap {
     int gs[3];
     fiesta_grid_size(h_, gs);
     grid_size_ = Eigen::Vector3i(gs[0], gs[1], gs[2]);
-    min_vec_ = Eigen::Vector3i(0, 0, 0);
-    max_vec_ = Eigen::Vector3i(gs[0] - 1, gs[1] - 1, gs[2] - 1);
   }
   ~ESDFMap() { fiesta_destroy(h_); }
   ESDFMap(const ESDFMap &) = delete;
@@ -72,7 +69,6 @@ class ESDFMap {
   // ESDFMap.h:124
   void SetParameters(double p_hit, double p_miss, double p_min, double p_max, double p_occ) {
     check(fiesta_set_parameters(h_, p_hit, p_miss, p_min, p_max, p_occ), "SetParameters");
-    min_occupancy_log_ = std::log(p_occ / (1 - p_occ));
   }
 
   // ESDFMap.h:128-130 -- the per-frame driver calls (Fiesta.h:507-514)
@@ -104,18 +100,8 @@ class ESDFMap {
   void SetUpdateRange(Eigen::Vector3d min_pos, Eigen::Vector3d max_pos, bool new_vec = true) {
     double a[3] = {min_pos(0), min_pos(1), min_pos(2)}, b[3] = {max_pos(0), max_pos(1), max_pos(2)};
     check(fiesta_set_update_range(h_, a, b, new_vec ? 1 : 0), "SetUpdateRange");
-    // host mirror of the box for the visualisation loops below (ESDFMap.cpp:794-809)
-    for (int i = 0; i < 3; ++i) {
-      double lo = std::max(min_pos(i), origin_(i)), hi = std::min(max_pos(i), origin_(i) + grid_size_(i) * resolution_);
-      min_vec_(i) = (int)std::floor((lo - origin_(i)) / resolution_);
-      max_vec_(i) = std::min((int)std::floor((hi - resolution_ / 2 - origin_(i)) / resolution_), grid_size_(i) - 1);
-    }
   }
-  void SetOriginalRange() {
-    check(fiesta_set_original_range(h_), "SetOriginalRange");
-    min_vec_ = Eigen::Vector3i(0, 0, 0);
-    max_vec_ = Eigen::Vector3i(grid_size_(0) - 1, grid_size_(1) - 1, grid_size_(2) - 1);
-  }
+  void SetOriginalRange() { check(fiesta_set_original_range(h_), "SetOriginalRange"); }
 
   // ---- additions (fast paths; not in the reference class) ----
   // One call for Fiesta::RaycastMultithread (Fiesta.h:281-303): `cloud` holds n points as packed float xyz in the sensor
@@ -128,23 +114,17 @@ class ESDFMap {
     check(fiesta_get_dist_grad_trilinear_batch(h_, pos_xyz, n, dist, grad_xyz), "GetDistWithGradTrilinearBatch");
   }
 
-  // ---- visualisation (ESDFMap.h:144-145; off the hot path: one device->host dump per call) ----
+  // ---- visualisation (ESDFMap.h:144-145): flag pass + ordered stream compaction on the device, only the selected points
+  // cross PCIe (fiesta_get_point_cloud / fiesta_get_slice_marker) ----
   void GetPointCloud(sensor_msgs::PointCloud &m, int vis_lower_bound, int vis_upper_bound) {
     m.header.frame_id = "world";
     m.points.clear();
-    std::vector<double> occ((size_t)grid_total_size_);
-    check(fiesta_export_occupancy(h_, occ.data()), "export_occupancy");
-    const int gyz = grid_size_(1) * grid_size_(2);
-    for (int x = min_vec_(0); x <= max_vec_(0); ++x)
-      for (int y = min_vec_(1); y <= max_vec_(1); ++y)
-        for (int z = std::max(min_vec_(2), vis_lower_bound); z <= std::min(max_vec_(2), vis_upper_bound); ++z)
-          if (occ[(size_t)x * gyz + (size_t)y * grid_size_(2) + z] > min_occupancy_log_) {
-            geometry_msgs::Point32 p;
-            p.x = (float)((x + 0.5) * resolution_ + origin_(0));
-            p.y = (float)((y + 0.5) * resolution_ + origin_(1));
-            p.z = (float)((z + 0.5) * resolution_ + origin_(2));
-            m.points.push_back(p);
-          }
+    int64_t n = 0;
+    check(fiesta_get_point_cloud(h_, vis_lower_bound, vis_upper_bound, nullptr, 0, &n), "GetPointCloud");
+    std::vector<float> xyz((size_t)n * 3 + 3);
+    if (n) check(fiesta_get_point_cloud(h_, vis_lower_bound, vis_upper_bound, xyz.data(), n, &n), "GetPointCloud");
+    m.points.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i) { m.points[i].x = xyz[3 * i]; m.points[i].y = xyz[3 * i + 1]; m.points[i].z = xyz[3 * i + 2]; }
   }
   void GetSliceMarker(visualization_msgs::Marker &m, int slice, int id, Eigen::Vector4d /*color*/, double max_dist) {
     m.header.frame_id = "world";
@@ -155,35 +135,17 @@ class ESDFMap {
     m.pose.orientation.w = 1; m.pose.orientation.x = m.pose.orientation.y = m.pose.orientation.z = 0;
     m.points.clear();
     m.colors.clear();
-    if (slice < 0 || slice >= grid_size_(2)) return;
-    std::vector<double> dist((size_t)grid_total_size_);
-    check(fiesta_export_distance(h_, dist.data()), "export_distance");
-    const int gyz = grid_size_(1) * grid_size_(2);
-    for (int x = min_vec_(0); x <= max_vec_(0); ++x)
-      for (int y = min_vec_(1); y <= max_vec_(1); ++y) {
-        const double d = dist[(size_t)x * gyz + (size_t)y * grid_size_(2) + slice];
-        if (d < 0 || d >= FIESTA_INFINITY) continue;
-        geometry_msgs::Point p;
-        p.x = (x + 0.5) * resolution_ + origin_(0); p.y = (y + 0.5) * resolution_ + origin_(1); p.z = (slice + 0.5) * resolution_ + origin_(2);
-        m.points.push_back(p);
-        m.colors.push_back(Rainbow(d <= max_dist ? d / max_dist : 1));
-      }
-  }
-
- private:
-  // HSV rainbow with s = v = 1 (same mapping as the reference's RainbowColorMap, ESDFMap.cpp:584-637)
-  static std_msgs::ColorRGBA Rainbow(double h) {
-    std_msgs::ColorRGBA c;
-    c.a = 1;
-    h = (h - std::floor(h)) * 6;
-    const int i = (int)std::floor(h);
-    double f = h - i;
-    if (!(i & 1)) f = 1 - f;
-    const float n = (float)(1 - f);
-    const float lut[7][3] = {{1, n, 0}, {n, 1, 0}, {0, 1, n}, {0, n, 1}, {n, 0, 1}, {1, 0, n}, {1, n, 0}};
-    const int k = (i >= 0 && i <= 6) ? i : 0;
-    c.r = lut[k][0]; c.g = lut[k][1]; c.b = lut[k][2];
-    return c;
+    int64_t n = 0;
+    check(fiesta_get_slice_marker(h_, slice, max_dist, nullptr, nullptr, 0, &n), "GetSliceMarker");
+    std::vector<double> xyz((size_t)n * 3 + 3);
+    std::vector<float> rgba((size_t)n * 4 + 4);
+    if (n) check(fiesta_get_slice_marker(h_, slice, max_dist, xyz.data(), rgba.data(), n, &n), "GetSliceMarker");
+    m.points.resize((size_t)n);
+    m.colors.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+      m.points[i].x = xyz[3 * i]; m.points[i].y = xyz[3 * i + 1]; m.points[i].z = xyz[3 * i + 2];
+      m.colors[i].r = rgba[4 * i]; m.colors[i].g = rgba[4 * i + 1]; m.colors[i].b = rgba[4 * i + 2]; m.colors[i].a = rgba[4 * i + 3];
+    }
   }
 };
 

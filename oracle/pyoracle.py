@@ -195,6 +195,21 @@ class OracleMap:
         return dict(occupancy_updates=s[0], inserts=s[1], deletes=s[2], expansions=s[3], change_num=s[4],
                     accumulator=s[5])
 
+    def GetPointCloud(self, lo, hi):
+        """Reference build only (kind == 'ref'): ESDFMap::GetPointCloud flattened to (n,3) float32."""
+        f = self._f("get_point_cloud"); f.restype = C.c_long
+        n = int(f(self._h, int(lo), int(hi), None, C.c_long(0)))
+        out = np.empty((n, 3), np.float32)
+        f(self._h, int(lo), int(hi), out.ctypes, C.c_long(n))
+        return out
+
+    def GetSliceMarker(self, slice_, max_dist):
+        f = self._f("get_slice_marker"); f.restype = C.c_long
+        n = int(f(self._h, int(slice_), C.c_double(max_dist), None, None, C.c_long(0)))
+        xyz, rgba = np.empty((n, 3)), np.empty((n, 4), np.float32)
+        f(self._h, int(slice_), C.c_double(max_dist), xyz.ctypes, rgba.ctypes, C.c_long(n))
+        return xyz, rgba
+
     def CheckConsistency(self):
         return bool(self._f("check_consistency")(self._h))
 

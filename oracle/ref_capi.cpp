@@ -232,6 +232,25 @@ void fiesta_ref_get_stats(void *h, long out[6]) {
   out[3] = r->last_expansions; out[4] = r->last_change_num; out[5] = r->map->total_time_;
 }
 
+// ESDFMap::GetPointCloud / GetSliceMarker (ESDFMap.cpp:544-582, 639-699) -- the reference's own code, results flattened.
+long fiesta_ref_get_point_cloud(void *h, int lo, int hi, float *out, long cap) {
+  sensor_msgs::PointCloud pc;
+  ((RefMap *)h)->map->GetPointCloud(pc, lo, hi);
+  long n = (long)pc.points.size();
+  for (long i = 0; i < n && i < cap; ++i) { out[3 * i] = pc.points[i].x; out[3 * i + 1] = pc.points[i].y; out[3 * i + 2] = pc.points[i].z; }
+  return n;
+}
+long fiesta_ref_get_slice_marker(void *h, int slice, double max_dist, double *xyz, float *rgba, long cap) {
+  visualization_msgs::Marker mk;
+  ((RefMap *)h)->map->GetSliceMarker(mk, slice, 100, Eigen::Vector4d(0, 1.0, 0, 1), max_dist);
+  long n = (long)mk.points.size();
+  for (long i = 0; i < n && i < cap; ++i) {
+    xyz[3 * i] = mk.points[i].x; xyz[3 * i + 1] = mk.points[i].y; xyz[3 * i + 2] = mk.points[i].z;
+    rgba[4 * i] = mk.colors[i].r; rgba[4 * i + 1] = mk.colors[i].g; rgba[4 * i + 2] = mk.colors[i].b; rgba[4 * i + 3] = mk.colors[i].a;
+  }
+  return n;
+}
+
 int fiesta_ref_check_consistency(void *h) {
   RefMap *r = (RefMap *)h;
   bool ok = false;
