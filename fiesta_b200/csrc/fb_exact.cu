@@ -12,7 +12,8 @@
 //    (dead / pulled code / pushes code) of the <= 25 elements that can write it: the lexicographic minimum (distance,
 //    timestamp) over their offers with timestamp < T that beat the snapshot -- exactly what a sequence of strict `>` tests
 //    in timestamp order leaves behind (x_state()).
-//  * An element's behaviour depends only on states at its own pop time (k_x_eval).  Starting from "everybody pushes its
+//  * An element's behaviour depends only on states at its own pop time (k_x_eval); it is kept, together with the entry's
+//    queue position, in one packed per-voxel word so that a reader learns everything about a potential writer with one load.  Starting from "everybody pushes its
 //    snapshot code", the behaviours are re-evaluated until none changes; element i is right once all elements before it
 //    are, so the fixpoint is the sequential execution (2-3 rounds in practice).
 //  * The last accepted write to a voxel in a generation is the lexicographic minimum over ALL offers; those writes, in
@@ -28,6 +29,8 @@
 //    delete_queue_ come out in the reference's order.
 #include <cub/cub.cuh>
 #include <stdio.h>
+#include <stdlib.h>
+#include <chrono>
 #include "fb_common.cuh"
 #include "fb_exact.h"
 
@@ -53,39 +56,43 @@ __device__ __forceinline__ unsigned x_dist_of(int x, int y, int z, uint32_t c) {
 
 struct XState { unsigned d; uint32_t c; unsigned ts; };
 
-// State of voxel (x,y,z) as seen at time T (exclusive) given the behaviours B of this generation's elements.
-__device__ __forceinline__ XState x_state(const FbGeom &g, const uint32_t *cobs, const uint32_t *M, const unsigned long long *B,
-                                          int x, int y, int z, unsigned T) {
+// Per-voxel packed word of the current generation: {queue position:27 | kind:2 | code:31}, all ones = no live entry here.
+// One 8-byte load tells a reader everything about a potential writer.
+#define XMB_NONE 0xffffffffffffffffull
+__device__ __forceinline__ unsigned long long x_mb(unsigned i, unsigned long long kind, uint32_t code) {
+  return ((unsigned long long)i << 33) | (kind << 31) | (unsigned long long)(code & FB_CODE_MASK);
+}
+__device__ __forceinline__ unsigned x_mb_idx(unsigned long long w) { return (unsigned)(w >> 33); }
+__device__ __forceinline__ unsigned long long x_mb_kind(unsigned long long w) { return (w >> 31) & 3ull; }
+__device__ __forceinline__ uint32_t x_mb_code(unsigned long long w) { return (uint32_t)(w & FB_CODE_MASK); }
+
+// State of voxel (x,y,z) as seen at time T (exclusive) given the behaviours of this generation's elements.
+__device__ __forceinline__ XState x_state(const FbGeom &g, const uint32_t *cobs, const unsigned long long *MB, int x, int y, int z, unsigned T) {
   XState s;
   const long long v = fb_ii(g, x, y, z);
   s.c = cobs[v] & FB_CODE_MASK; s.d = x_dist_of(x, y, z, s.c); s.ts = XNONE;
   const unsigned d0 = s.d;
   if (s.c == FB_UNKNOWN) return s;                             // never observed: distance_ = -10000 is never > tmp (:382)
   if (!fb_in_range(g, x, y, z)) return s;                     // pushes only go to voxels inside the update box (:378)
-#pragma unroll 4
+#pragma unroll 8
   for (int k = 0; k < 24; ++k) {
     const int qx = x - x_dirs[k][0], qy = y - x_dirs[k][1], qz = z - x_dirs[k][2];
     if (!fb_in_grid(g, qx, qy, qz)) continue;
-    const unsigned j = M[fb_ii(g, qx, qy, qz)];
-    if (j == XNONE) continue;
-    const unsigned long long b = B[j];
-    if ((b >> 32) != X_PUSH) continue;
-    const unsigned ts = j * 32u + (unsigned)k;
+    const unsigned long long w = MB[fb_ii(g, qx, qy, qz)];
+    if (w == XMB_NONE || x_mb_kind(w) != X_PUSH) continue;
+    const unsigned ts = x_mb_idx(w) * 32u + (unsigned)k;
     if (ts >= T) continue;
-    const uint32_t c = (uint32_t)b;
+    const uint32_t c = x_mb_code(w);
     const unsigned d = x_d2(x, y, z, c);
     if (d < d0 && (d < s.d || (d == s.d && ts < s.ts))) { s.d = d; s.c = c; s.ts = ts; }
   }
-  const unsigned j = M[v];
-  if (j != XNONE) {
-    const unsigned long long b = B[j];
-    if ((b >> 32) == X_PULL) {
-      const unsigned ts = j * 32u + 24u;
-      if (ts < T) {
-        const uint32_t c = (uint32_t)b;
-        const unsigned d = x_d2(x, y, z, c);
-        if (d < d0 && (d < s.d || (d == s.d && ts < s.ts))) { s.d = d; s.c = c; s.ts = ts; }
-      }
+  const unsigned long long w = MB[v];
+  if (w != XMB_NONE && x_mb_kind(w) == X_PULL) {
+    const unsigned ts = x_mb_idx(w) * 32u + 24u;
+    if (ts < T) {
+      const uint32_t c = x_mb_code(w);
+      const unsigned d = x_d2(x, y, z, c);
+      if (d < d0 && (d < s.d || (d == s.d && ts < s.ts))) { s.d = d; s.c = c; s.ts = ts; }
     }
   }
   return s;
@@ -132,14 +139,13 @@ __global__ void k_x_flag_exist(const uint32_t *list, unsigned n, const double *o
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) flags[i] = ((occ[list[i]] > l_occ) ? 1 : 0) == want;
 }
-__global__ void k_x_apply_seed(FbGeom g, const uint32_t *E, unsigned n, uint32_t *cobs, uint32_t *M, unsigned long long *LS, unsigned long long t0) {
+__global__ void k_x_apply_seed(FbGeom g, const uint32_t *E, unsigned n, uint32_t *cobs, unsigned long long *LS, unsigned long long t0) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t ii = E[i];
   int x, y, z; x_coords(g, ii, x, y, z);
   cobs[ii] = fb_pack(x, y, z);                                 // closest_obstacle_ = self, distance_ = 0 (:286-287)
   LS[ii] = t0 + i;                                             // InsertIntoList(idx, idx) (:288)
-  M[ii] = i;
 }
 
 // ------------------------------------------------------------------ E2: delete
@@ -215,88 +221,138 @@ __global__ void k_x_apply_reseed(const uint32_t *deps, unsigned n, const uint32_
   LS[deps[i]] = t0 + i;                                        // InsertIntoList(new_obs_idx, obs_idx) (:333)
   flags[i] = nc[i] >= 2u;                                      // `if (distance < infinity_) update_queue_.push` (:329-331)
 }
-__global__ void k_x_set_M(const uint32_t *E, unsigned first, unsigned n, uint32_t *M) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) M[E[first + i]] = first + i;
-}
-
 // ------------------------------------------------------------------ E3: relax, one FIFO generation at a time
-__global__ void k_x_init_beh(const uint32_t *E, unsigned n, const uint32_t *cobs, unsigned long long *B) {
+// Initial guess of the behaviour fixpoint: every entry is live and pushes its snapshot code.
+__global__ void k_x_init_beh(const uint32_t *E, unsigned n, const uint32_t *cobs, unsigned long long *MB) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) B[i] = (X_PUSH << 32) | (cobs[E[i]] & FB_CODE_MASK);
+  if (i < n) MB[E[i]] = x_mb(i, X_PUSH, cobs[E[i]]);
 }
 // One round of the behaviour fixpoint.  B is updated IN PLACE (elements evaluated later in the same round already see the
 // new behaviour of earlier ones); an element is re-evaluated only in the first round of a generation or when an element
 // within reach (<= 4 voxels: its own 8^3 tile or one of the 26 around it) changed its behaviour in the previous round.
 // The loop ends with a round in which nothing changed, which reads a stable B: that state is the sequential execution.
-__global__ void k_x_eval(FbGeom g, const uint32_t *E, unsigned n, const uint32_t *cobs, const uint32_t *M, unsigned long long *B,
-                         uint32_t *tdirty, unsigned stamp, int first_round, unsigned *changed) {
+__global__ void k_x_eval(FbGeom g, const uint32_t *E, unsigned n, const uint32_t *cobs, unsigned long long *MB, uint32_t *tdirty,
+                         unsigned stamp, int first_round, unsigned *changed) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int x, y, z; x_coords(g, E[i], x, y, z);
+  const uint32_t p = E[i];
+  int x, y, z; x_coords(g, p, x, y, z);
   const int tx = x >> 3, ty = y >> 3, tz = z >> 3;
   if (!first_round && tdirty[(tx * g.ty + ty) * g.tz + tz] != stamp) return;
   const unsigned T0 = i * 32u;
-  const XState s = x_state(g, cobs, M, B, x, y, z, T0);
-  const uint32_t c0 = cobs[E[i]] & FB_CODE_MASK;
+  const XState s = x_state(g, cobs, MB, x, y, z, T0);
+  const uint32_t c0 = cobs[p] & FB_CODE_MASK;
   unsigned long long nb;
-  if (s.d != x_dist_of(x, y, z, c0)) nb = X_DEAD << 32;       // `xx.distance_ != distance_buffer_[idx]`: stale (:345)
+  if (s.d != x_dist_of(x, y, z, c0)) nb = x_mb(i, X_DEAD, 0);  // `xx.distance_ != distance_buffer_[idx]`: stale (:345)
   else {
     unsigned curd = s.d; uint32_t curc = s.c; bool ch = false;
     for (int k = 0; k < 24; ++k) {                             // pull phase (:349-367)
       const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
       if (!fb_in_range(g, nx, ny, nz) || !fb_in_grid(g, nx, ny, nz)) continue;
-      const XState sn = x_state(g, cobs, M, B, nx, ny, nz, T0);
+      const XState sn = x_state(g, cobs, MB, nx, ny, nz, T0);
       if (sn.c < 2u) continue;
       const unsigned t = x_d2(x, y, z, sn.c);
       if (curd > t) { curd = t; curc = sn.c; ch = true; }
     }
-    nb = ch ? ((X_PULL << 32) | curc) : ((X_PUSH << 32) | s.c);
+    nb = ch ? x_mb(i, X_PULL, curc) : x_mb(i, X_PUSH, s.c);
   }
-  if (nb != B[i]) {
-    B[i] = nb;
+  if (nb != MB[p]) {
+    MB[p] = nb;
     *changed = 1u;
     for (int a = max(tx - 1, 0); a <= min(tx + 1, g.tx - 1); ++a)
       for (int b = max(ty - 1, 0); b <= min(ty + 1, g.ty - 1); ++b)
         for (int c = max(tz - 1, 0); c <= min(tz + 1, g.tz - 1); ++c) tdirty[(a * g.ty + b) * g.tz + c] = stamp + 1u;
   }
 }
+// The same evaluation with one WARP per element, for the rounds after the first: only the few elements in dirty tiles do
+// any work there, so the round's duration is the latency of a single evaluation -- 25 state queries run on 25 lanes
+// instead of one after the other.  The sequential pull loop "for k: if (dist > tmp) take" (:349-367) is the lexicographic
+// minimum (tmp, k) over the neighbours that beat the own distance (warp reduction).
+// Elements whose tile is dirty for this round -> work list (so that the evaluation kernel is not launched over millions
+// of idle threads).
+__global__ void k_x_collect(FbGeom g, const uint32_t *E, unsigned n, const uint32_t *tdirty, unsigned stamp, uint32_t *work, unsigned *nwork) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool on = false;
+  if (i < n) { int x, y, z; x_coords(g, E[i], x, y, z); on = tdirty[((x >> 3) * g.ty + (y >> 3)) * g.tz + (z >> 3)] == stamp; }
+  const unsigned slot = fb_warp_append(nwork, on);
+  if (on) work[slot] = i;
+}
+__global__ void k_x_eval_warp(FbGeom g, const uint32_t *E, const uint32_t *work, const unsigned *nwork, const uint32_t *cobs, unsigned long long *MB,
+                              uint32_t *tdirty, unsigned stamp, unsigned *changed) {
+  const unsigned lane = threadIdx.x & 31u, nw = *nwork;
+  for (unsigned wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < nw; wi += (gridDim.x * blockDim.x) >> 5) {
+  const unsigned i = work[wi];
+  const uint32_t p = E[i];
+  int x, y, z; x_coords(g, p, x, y, z);
+  const int tx = x >> 3, ty = y >> 3, tz = z >> 3;
+  const unsigned T0 = i * 32u;
+  int qx = x, qy = y, qz = z;
+  bool valid = lane == 24;
+  if (lane < 24) { qx += x_dirs[lane][0]; qy += x_dirs[lane][1]; qz += x_dirs[lane][2]; valid = fb_in_range(g, qx, qy, qz) && fb_in_grid(g, qx, qy, qz); }
+  XState st; st.d = 0xffffffffu; st.c = 0; st.ts = XNONE;
+  if (valid) st = x_state(g, cobs, MB, qx, qy, qz, T0);      // lanes 0..23: neighbour k at pop time; lane 24: the element itself
+  const unsigned sd = __shfl_sync(0xffffffffu, st.d, 24);
+  const uint32_t sc = __shfl_sync(0xffffffffu, st.c, 24);
+  const uint32_t c0 = cobs[p] & FB_CODE_MASK;
+  unsigned long long nb;
+  if (sd != x_dist_of(x, y, z, c0)) nb = x_mb(i, X_DEAD, 0);
+  else {
+    unsigned long long key = ~0ull;
+    if (lane < 24 && valid && st.c >= 2u) {
+      const unsigned t = x_d2(x, y, z, st.c);
+      if (t < sd) key = ((unsigned long long)t << 8) | lane;
+    }
+    unsigned long long best = key;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o); best = other < best ? other : best; }
+    if (best == ~0ull) nb = x_mb(i, X_PUSH, sc);
+    else nb = x_mb(i, X_PULL, __shfl_sync(0xffffffffu, st.c, (int)(best & 0xffu)));
+  }
+  if (lane == 0 && nb != MB[p]) {
+    MB[p] = nb;
+    *changed = 1u;
+    for (int a = max(tx - 1, 0); a <= min(tx + 1, g.tx - 1); ++a)
+      for (int b = max(ty - 1, 0); b <= min(ty + 1, g.ty - 1); ++b)
+        for (int c = max(tz - 1, 0); c <= min(tz + 1, g.tz - 1); ++c) tdirty[(a * g.ty + b) * g.tz + c] = stamp + 1u;
+  }
+  }
+}
 // Final writes of the generation -> slots (timestamp order) of the next generation's queue.
-__global__ void k_x_commit(FbGeom g, const uint32_t *E, unsigned n, const uint32_t *cobs, const uint32_t *M, const unsigned long long *B,
+__global__ void k_x_commit(FbGeom g, const uint32_t *E, unsigned n, const uint32_t *cobs, const unsigned long long *MB,
                            uint32_t *slotv, uint32_t *slotc, uint8_t *slotf, unsigned long long *expansions) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < n && (B[i] >> 32) != X_DEAD;
+  unsigned long long b = XMB_NONE;
+  if (i < n) b = MB[E[i]];
+  const bool live = i < n && x_mb_kind(b) != X_DEAD;
   const unsigned nlive = __popc(__ballot_sync(0xffffffffu, live));
   if ((threadIdx.x & 31) == 0 && nlive) atomicAdd(expansions, (unsigned long long)nlive);   // `times++` (:347)
   if (!live) return;
   int x, y, z; x_coords(g, E[i], x, y, z);
-  const unsigned long long b = B[i];
-  if ((b >> 32) == X_PUSH) {
+  if (x_mb_kind(b) == X_PUSH) {
     for (int k = 0; k < 24; ++k) {                             // push phase (:375-391)
       const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
       if (!fb_in_range(g, nx, ny, nz) || !fb_in_grid(g, nx, ny, nz)) continue;
-      const XState f = x_state(g, cobs, M, B, nx, ny, nz, XNONE);
+      const XState f = x_state(g, cobs, MB, nx, ny, nz, XNONE);
       const unsigned ts = i * 32u + (unsigned)k;
       if (f.ts == ts) { slotv[ts] = (uint32_t)fb_ii(g, nx, ny, nz); slotc[ts] = f.c; slotf[ts] = 1; }
     }
   } else {
-    const XState f = x_state(g, cobs, M, B, x, y, z, XNONE);
+    const XState f = x_state(g, cobs, MB, x, y, z, XNONE);
     const unsigned ts = i * 32u + 24u;
     if (f.ts == ts) { slotv[ts] = E[i]; slotc[ts] = f.c; slotf[ts] = 1; }
   }
 }
-__global__ void k_x_clear_M(const uint32_t *E, unsigned n, uint32_t *M) {
+__global__ void k_x_clear_M(const uint32_t *E, unsigned n, unsigned long long *MB) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) M[E[i]] = XNONE;
+  if (i < n) MB[E[i]] = XMB_NONE;
 }
-__global__ void k_x_apply(const uint32_t *sel, unsigned n, const uint32_t *slotv, const uint32_t *slotc, uint32_t *cobs, uint32_t *M,
+__global__ void k_x_apply(const uint32_t *sel, unsigned n, const uint32_t *slotv, const uint32_t *slotc, uint32_t *cobs,
                           unsigned long long *LS, unsigned long long t0, uint32_t *Enext) {
   const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const uint32_t s = sel[r], v = slotv[s];
   cobs[v] = slotc[s];
   LS[v] = t0 + s;                                              // every accepted write relinks the voxel at its list's front
-  M[v] = r;
   Enext[r] = v;
 }
 __global__ void k_x_fill32(uint32_t *a, size_t n, uint32_t val) {
@@ -358,20 +414,20 @@ static cudaError_t x_flag(FbExact *X, cudaStream_t s, unsigned *out) {   // read
 cudaError_t fb_exact_init(FbExact *X, const FbGeom &g, cudaStream_t s) {
   memset(X, 0, sizeof(*X));
   const size_t P = (size_t)g.ptotal;
-  XCK(cudaMalloc((void **)&X->M, P * 4)); XCK(cudaMalloc((void **)&X->LS, P * 8)); XCK(cudaMalloc((void **)&X->tkey, P * 8));
+  XCK(cudaMalloc((void **)&X->MB, P * 8)); XCK(cudaMalloc((void **)&X->LS, P * 8)); XCK(cudaMalloc((void **)&X->tkey, P * 8));
   XCK(cudaMalloc((void **)&X->touched, P * 4));
   XCK(cudaMalloc((void **)&X->tdirty, (size_t)g.ntiles * 4)); XCK(cudaMemsetAsync(X->tdirty, 0, (size_t)g.ntiles * 4, s));
   XCK(cudaMalloc((void **)&X->d_count, 16)); XCK(cudaMalloc((void **)&X->d_flag, 16));
   XCK(cudaMallocHost((void **)&X->h_count, 16));
   XCK(cudaMemsetAsync(X->d_count, 0, 16, s)); XCK(cudaMemsetAsync(X->d_flag, 0, 16, s));
-  k_x_fill32<<<148 * 8, 256, 0, s>>>(X->M, P, XNONE);
+  k_x_fill64<<<148 * 8, 256, 0, s>>>(X->MB, P, XMB_NONE);
   k_x_fill64<<<148 * 8, 256, 0, s>>>(X->tkey, P, ~0ull);
   XCK(cudaMemsetAsync(X->LS, 0, P * 8, s));
   X->tclock = 1; X->key_base = 0; X->eval_clock = 1;
   return cudaGetLastError();
 }
 void fb_exact_free(FbExact *X) {
-  void *p[] = {X->M, X->LS, X->tkey, X->touched, X->tdirty, X->d_count, X->d_flag, X->E[0], X->E[1], X->B[0], X->B[1], X->slotv, X->slotc, X->slotf, X->sel,
+  void *p[] = {X->MB, X->LS, X->tkey, X->touched, X->tdirty, X->d_count, X->d_flag, X->E[0], X->E[1], X->slotv, X->slotc, X->slotf, X->sel,
                X->k1, X->k2, X->k1b, X->k2b, X->dv, X->idx[0], X->idx[1], X->deps, X->nc[0], X->nc[1], X->flags, X->flags2, X->cub_tmp};
   for (void *q : p) if (q) cudaFree(q);
   if (X->h_count) cudaFreeHost(X->h_count);
@@ -428,7 +484,7 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
   if (n_ins) {
     k_x_flag_exist<<<nblk(n_ins), 256, 0, s>>>(ins, n_ins, occ, l_occ, X->flags, 1);
     if ((e = x_select(X, ins, X->flags, X->E[0], n_ins, &nE, s))) return e;
-    if (nE) k_x_apply_seed<<<nblk(nE), 256, 0, s>>>(g, X->E[0], nE, cobs, X->M, X->LS, X->tclock);
+    if (nE) k_x_apply_seed<<<nblk(nE), 256, 0, s>>>(g, X->E[0], nE, cobs, X->LS, X->tclock);
     X->tclock += nE;
     *launches += 2;
   }
@@ -494,7 +550,6 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
         if (nE) XCK(cudaMemcpyAsync(X->E[1], X->E[0], (size_t)nE * 4, cudaMemcpyDeviceToDevice, s));
         unsigned nr = 0;
         if ((e = x_select(X, X->deps, X->flags, X->E[1] + nE, ndep, &nr, s))) return e;
-        if (nr) k_x_set_M<<<nblk(nr), 256, 0, s>>>(X->E[1], nE, nr, X->M);
         // keep the generation-0 list in E[0]
         if ((e = x_ensure(X, &X->E[0], &X->cap_E[0], (size_t)nE + nr + 16))) return e;
         XCK(cudaMemcpyAsync(X->E[0], X->E[1], (size_t)(nE + nr) * 4, cudaMemcpyDeviceToDevice, s));
@@ -504,32 +559,46 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
     }
   }
   // ---- E3: relax (:338-392)
+  static const bool xdbg = getenv("FIESTA_DEBUG_X") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  double t_eval = 0, t_commit = 0, t_select = 0, t_apply = 0; auto t_start = now();
   int cur = 0;
   XCK(cudaMemsetAsync(X->d_count + 2, 0, 8, s));               // expansions counter (u64 at d_count[2..3])
   while (nE) {
     st->generations++;
     const size_t nslots = (size_t)nE * 32;
     if (nE >= (1u << 27)) { snprintf(X->err, sizeof(X->err), "exact mode: generation with more than 2^27 entries"); return cudaErrorInvalidValue; }
-    if ((e = x_ensure(X, &X->B[0], &X->cap_B[0], nE))) return e;
-    if ((e = x_ensure(X, &X->B[1], &X->cap_B[1], nE))) return e;
     if ((e = x_ensure(X, &X->slotv, &X->cap_slotv, nslots))) return e;
     if ((e = x_ensure(X, &X->slotc, &X->cap_slotc, nslots))) return e;
     if ((e = x_ensure(X, &X->slotf, &X->cap_slotf, nslots))) return e;
     if ((e = x_ensure(X, &X->sel, &X->cap_sel, nslots))) return e;
-    k_x_init_beh<<<nblk(nE), 256, 0, s>>>(X->E[cur], nE, cobs, X->B[0]);
-    const int b = 0;
-    for (int it = 0; it < 100000; ++it) {
-      ++X->eval_clock;
-      k_x_eval<<<nblk(nE, 128), 128, 0, s>>>(g, X->E[cur], nE, cobs, X->M, X->B[0], X->tdirty, X->eval_clock, it == 0, X->d_flag);
-      *launches += 1;
+    auto t0 = now();
+    k_x_init_beh<<<nblk(nE), 256, 0, s>>>(X->E[cur], nE, cobs, X->MB);
+    // Rounds are launched four at a time between host checks: a round after convergence finds no dirty tile and costs
+    // next to nothing, and a batch that changed nothing proves that the last state survived a full round.
+    for (int it = 0; it < 100000; it += 4) {
+      for (int q = 0; q < 4; ++q) {
+        ++X->eval_clock;
+        if (it + q == 0) k_x_eval<<<nblk(nE, 128), 128, 0, s>>>(g, X->E[cur], nE, cobs, X->MB, X->tdirty, X->eval_clock, 1, X->d_flag);
+        else {
+          XCK(cudaMemsetAsync(X->d_count + 1, 0, 4, s));
+          k_x_collect<<<nblk(nE), 256, 0, s>>>(g, X->E[cur], nE, X->tdirty, X->eval_clock, X->sel, X->d_count + 1);
+          k_x_eval_warp<<<148 * 4, 256, 0, s>>>(g, X->E[cur], X->sel, X->d_count + 1, cobs, X->MB, X->tdirty, X->eval_clock, X->d_flag);
+        }
+      }
+      *launches += 4;
       unsigned ch = 0;
       if ((e = x_flag(X, s, &ch))) return e;
-      st->eval_rounds++;
+      st->eval_rounds += 4;
       if (!ch) break;
     }
+    auto t1 = now();
     XCK(cudaMemsetAsync(X->slotf, 0, nslots, s));
-    k_x_commit<<<nblk(nE, 128), 128, 0, s>>>(g, X->E[cur], nE, cobs, X->M, X->B[b], X->slotv, X->slotc, X->slotf, (unsigned long long *)(X->d_count + 2));
-    k_x_clear_M<<<nblk(nE), 256, 0, s>>>(X->E[cur], nE, X->M);
+    k_x_commit<<<nblk(nE, 128), 128, 0, s>>>(g, X->E[cur], nE, cobs, X->MB, X->slotv, X->slotc, X->slotf, (unsigned long long *)(X->d_count + 2));
+    k_x_clear_M<<<nblk(nE), 256, 0, s>>>(X->E[cur], nE, X->MB);
+    if (xdbg) cudaStreamSynchronize(s);
+    auto t2 = now();
     unsigned n2 = 0;
     {
       size_t bytes = 0;
@@ -541,9 +610,13 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
       XCK(cudaStreamSynchronize(s));
       n2 = *X->h_count;
     }
+    auto t3 = now();
     if ((e = x_ensure(X, &X->E[cur ^ 1], &X->cap_E[cur ^ 1], (size_t)n2 + 16))) return e;
-    if (n2) k_x_apply<<<nblk(n2), 256, 0, s>>>(X->sel, n2, X->slotv, X->slotc, cobs, X->M, X->LS, X->tclock, X->E[cur ^ 1]);
+    if (n2) k_x_apply<<<nblk(n2), 256, 0, s>>>(X->sel, n2, X->slotv, X->slotc, cobs, X->LS, X->tclock, X->E[cur ^ 1]);
     *launches += 5;
+    if (xdbg) cudaStreamSynchronize(s);
+    auto t4 = now();
+    t_eval += ms(t0, t1); t_commit += ms(t1, t2); t_select += ms(t2, t3); t_apply += ms(t3, t4);
     X->tclock += nslots + 1;
     st->voxels_changed += n2;
     cur ^= 1;
@@ -552,5 +625,6 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
   XCK(cudaMemcpyAsync(X->h_count, X->d_count + 2, 8, cudaMemcpyDeviceToHost, s));
   XCK(cudaStreamSynchronize(s));
   st->expansions = *(unsigned long long *)X->h_count;
+  if (xdbg) fprintf(stderr, "[x] gens %u rounds %u deps %u | relax %.1f ms: eval %.1f commit %.1f select %.1f apply %.1f\n", st->generations, st->eval_rounds, st->dependants, ms(t_start, now()), t_eval, t_commit, t_select, t_apply);
   return cudaSuccess;
 }

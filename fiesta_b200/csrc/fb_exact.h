@@ -9,7 +9,7 @@ struct FbExactStats {
 };
 
 struct FbExact {
-  uint32_t *M;                 // per voxel: position of its live entry in the current FIFO generation
+  unsigned long long *MB;      // per voxel: {queue position | behaviour | code} of its live entry in the current generation
   unsigned long long *LS;      // per voxel: time of the last relink into a dependant list
   unsigned long long *tkey;    // per voxel: serial time of the first pending observation
   uint32_t *touched;           // voxels with pending observations (unordered; ordered by tkey at integration)
@@ -19,7 +19,6 @@ struct FbExact {
   uint32_t *tdirty;            // per 8^3 tile: evaluation round in which its elements must be re-evaluated
   unsigned eval_clock;
   uint32_t *E[2]; size_t cap_E[2];
-  unsigned long long *B[2]; size_t cap_B[2];
   uint32_t *slotv, *slotc, *sel; uint8_t *slotf; size_t cap_slotv, cap_slotc, cap_sel, cap_slotf;
   unsigned long long *k1, *k2, *k1b, *k2b; size_t cap_k1, cap_k2, cap_k1b, cap_k2b;
   uint32_t *dv, *idx[2], *deps, *nc[2]; size_t cap_dv, cap_idx[2], cap_deps, cap_nc[2];
