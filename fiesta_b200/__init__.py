@@ -56,7 +56,7 @@ SYMBOLS = [
     "fiesta_get_distance_pos", "fiesta_get_distance_vox", "fiesta_get_occupancy_pos", "fiesta_get_occupancy_vox",
     "fiesta_get_dist_grad_trilinear", "fiesta_get_distance_batch_pos", "fiesta_get_dist_grad_trilinear_batch",
     "fiesta_export_distance", "fiesta_export_closest_obstacle", "fiesta_export_occupancy", "fiesta_export_counters",
-    "fiesta_get_stats", "fiesta_synchronize", "fiesta_set_shard", "fiesta_shard_pack", "fiesta_shard_ingest", "fiesta_shard_relax", "fiesta_get_point_cloud", "fiesta_get_slice_marker",
+    "fiesta_get_stats", "fiesta_synchronize", "fiesta_set_shard", "fiesta_shard_pack", "fiesta_shard_ingest", "fiesta_shard_relax", "fiesta_get_point_cloud", "fiesta_get_slice_marker", "fiesta_set_occupancy_batch_vox_device",
 ]
 
 _lib = None
@@ -152,6 +152,10 @@ class ESDFMap:
         self._ck(self._L.fiesta_set_occupancy_batch_pos(self._h, pos.ctypes, occ.ctypes, C.c_int64(len(pos)), out.ctypes),
                  "SetOccupancy batch")
         return out
+
+    def SetOccupancyBatchVoxDevice(self, d_vox_ptr, d_occ_ptr, n):
+        self._ck(self._L.fiesta_set_occupancy_batch_vox_device(self._h, C.c_void_p(int(d_vox_ptr)), C.c_void_p(int(d_occ_ptr)), C.c_int64(int(n))),
+                 "SetOccupancy batch (device)")
 
     def CheckUpdate(self):
         return bool(self._L.fiesta_check_update(self._h))

@@ -93,6 +93,15 @@ __global__ void k_apply_events(FbGeom g, const uint32_t *ev, size_t n, FbTouch t
   fb_touch(g, t, e & 0x7fffffffu, e >> 31, key_base + i);       // the i-th staged call = its position in the serial order
 }
 
+// SetOccupancy(Vector3i, occ) for events that are already on the device (ESDFMap.cpp:417-437).
+__global__ void k_apply_vox_events(FbGeom g, const int *vox, const uint8_t *occ, long long n, FbTouch t) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = vox[3 * i], y = vox[3 * i + 1], z = vox[3 * i + 2];
+  if (!fb_in_range(g, x, y, z) || !fb_in_grid(g, x, y, z)) return;       // `if (!VoxInRange(vox)) return idx;` (:420-421)
+  fb_touch(g, t, (unsigned)fb_ii(g, x, y, z), occ[i] & 1u, 0ull);
+}
+
 // O2: ESDFMap::UpdateOccupancy (ESDFMap.cpp:235-271).  One 128-thread CTA streams the counters of one queued 8^3 tile
 // (4 voxels = one 32-byte sector per thread); every voxel with pending observations is integrated exactly as the
 // reference does.  Voxels are independent, so the queue order does not matter for the result.
@@ -457,6 +466,20 @@ int fiesta_set_occupancy_batch_pos(fiesta_map *m, const double *pos, const uint8
     }
     if (out_idx) out_idx[i] = ret;
   }
+  return FIESTA_OK;
+}
+
+int fiesta_set_occupancy_batch_vox_device(fiesta_map *m, const int *d_vox, const uint8_t *d_occ, int64_t n) {
+  if (!m || n < 0 || (n > 0 && (!d_vox || !d_occ))) return FIESTA_ERR_INVALID;
+  if (m->mode != FIESTA_MODE_FAST) { set_error("fiesta_set_occupancy_batch_vox_device: FAST mode only (device events carry no serial order)"); return FIESTA_ERR_INVALID; }
+  if (n == 0) return FIESTA_OK;
+  CK(cudaSetDevice(m->device));
+  FbTouch t = {m->cnt, m->touch_flag, m->touch_list, m->touch_epoch, m->d_ctr, nullptr, nullptr};
+  k_apply_vox_events<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->g, d_vox, d_occ, n, t);
+  m->st.kernel_launches++;
+  CK(cudaGetLastError());
+  int r;
+  if ((r = fetch_counters(m))) return r;
   return FIESTA_OK;
 }
 

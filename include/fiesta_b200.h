@@ -103,6 +103,10 @@ int fiesta_set_occupancy_vox(fiesta_map *m, const int vox[3], int occ);
 int fiesta_set_occupancy_batch_pos(fiesta_map *m, const double *pos_xyz, const uint8_t *occ, int64_t n, int *out_idx);
 int fiesta_set_occupancy_batch_vox(fiesta_map *m, const int *vox_xyz, const uint8_t *occ, int64_t n, int *out_idx);
 
+/* SetOccupancy(Vector3i, occ) for n events whose arrays already live in DEVICE memory (vox: 3 ints each, occ: 0/1); events
+ * outside the update box or the grid are ignored exactly like the host call ignores them.  FAST mode only (no serial order). */
+int fiesta_set_occupancy_batch_vox_device(fiesta_map *m, const int *d_vox_xyz, const uint8_t *d_occ, int64_t n);
+
 /* Fiesta::RaycastMultithread + RaycastProcess, serial semantics (Fiesta.h:194-303), fused with Raycast()
  * (raycast.cpp:56-158) and the counter part of SetOccupancy.  xyz: n points (pcl::PointXYZ, 3 floats each) in the
  * sensor frame; T: row-major 4x4 `transform_` (Fiesta.h:415-419); raycast_origin_ = T[:3,3]/T[3,3] (Fiesta.h:420).

@@ -106,3 +106,28 @@ def test_local_update_box(oracle_built, mode):
             assert res["cobs_tie"] == 0, (r, res)
     for m in (dev, ora):
         m.SetOriginalRange()
+
+
+def test_device_resident_event_batch(oracle_built):
+    """fiesta_set_occupancy_batch_vox_device == the host SetOccupancy loop (events already in HBM; dynamic-obstacle stress path)."""
+    import torch
+    dev, ora = pair(oracle_built, "fast", params=scenes.PARAMS_TOGGLE)
+    allv = scenes.all_voxels(dev.grid_size)
+    for m in (dev, ora):
+        m.SetOccupancyBatchVox(allv, np.zeros(len(allv), np.uint8)); m.UpdateOccupancy(True); m.UpdateESDF()
+    rng = np.random.default_rng(4)
+    state = np.zeros(len(allv), np.uint8)
+    for f in range(3):
+        idx = rng.choice(len(allv), len(allv) // 5, replace=False)
+        occ = (1 - state[idx]).astype(np.uint8); state[idx] = occ
+        vox = np.concatenate([allv[idx], np.array([[-1, 0, 0], [10 ** 6, 2, 3]], np.int32)])   # + out-of-grid events: ignored
+        occ2 = np.concatenate([occ, np.array([1, 1], np.uint8)])
+        tv, to = torch.from_numpy(vox).cuda(), torch.from_numpy(occ2).cuda()
+        dev.SetOccupancyBatchVoxDevice(tv.data_ptr(), to.data_ptr(), len(vox))
+        ora.SetOccupancyBatchVox(allv[idx], occ)
+        assert same_counters(dev, ora)
+        assert dev.CheckUpdate() == ora.CheckUpdate()
+        assert dev.UpdateOccupancy(True) == ora.UpdateOccupancy(True)
+        dev.UpdateESDF(); ora.UpdateESDF()
+        r = compare(dev, ora)
+        assert r["occ"] == 0 and r["dist"] == 0 and r["cobs_nontie"] == 0, (f, r)
