@@ -32,6 +32,12 @@ class RaycastParams(C.Structure):
     _fields_ = [("min_ray_length", C.c_double), ("max_ray_length", C.c_double)]
 
 
+class DepthParams(C.Structure):
+    _fields_ = [("focal_x", C.c_double), ("focal_y", C.c_double), ("center_x", C.c_double), ("center_y", C.c_double), ("use_depth_filter", C.c_int32),
+                ("depth_filter_margin", C.c_int32), ("depth_filter_max_dist", C.c_double), ("depth_filter_min_dist", C.c_double),
+                ("depth_filter_tolerance", C.c_double)]
+
+
 class ShardInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("rank", "world", "x_begin", "x_end", "has_lo", "has_hi")] + [("layer_words", C.c_int64)]
 
@@ -56,7 +62,7 @@ SYMBOLS = [
     "fiesta_get_distance_pos", "fiesta_get_distance_vox", "fiesta_get_occupancy_pos", "fiesta_get_occupancy_vox",
     "fiesta_get_dist_grad_trilinear", "fiesta_get_distance_batch_pos", "fiesta_get_dist_grad_trilinear_batch",
     "fiesta_export_distance", "fiesta_export_closest_obstacle", "fiesta_export_occupancy", "fiesta_export_counters",
-    "fiesta_get_stats", "fiesta_synchronize", "fiesta_set_shard", "fiesta_shard_pack", "fiesta_shard_ingest", "fiesta_shard_relax", "fiesta_get_point_cloud", "fiesta_get_slice_marker", "fiesta_set_occupancy_batch_vox_device",
+    "fiesta_get_stats", "fiesta_synchronize", "fiesta_set_shard", "fiesta_shard_pack", "fiesta_shard_ingest", "fiesta_shard_relax", "fiesta_get_point_cloud", "fiesta_get_slice_marker", "fiesta_set_occupancy_batch_vox_device", "fiesta_depth_frame", "fiesta_last_depth_cloud",
 ]
 
 _lib = None
@@ -224,6 +230,25 @@ class ESDFMap:
         T = _f64(T).reshape(16)
         self._ck(self._L.fiesta_raycast_frame(self._h, C.c_void_p(int(host_ptr)), C.c_int64(int(n)), T.ctypes, C.byref(p)),
                  "RaycastFrame")
+
+    # --- Fiesta::DepthConversion + RaycastMultithread (Fiesta.h:319-382, 281-303) ---
+    def DepthFrame(self, depth_u16, dparams, T, m_rel, min_ray_length, max_ray_length):
+        img = np.ascontiguousarray(depth_u16, dtype=np.uint16)
+        rp = RaycastParams(float(min_ray_length), float(max_ray_length))
+        T = _f64(T).reshape(16)
+        mr = _f64(m_rel if m_rel is not None else np.eye(4)).reshape(16)
+        n = C.c_int64(0)
+        self._ck(self._L.fiesta_depth_frame(self._h, img.ctypes, int(img.shape[0]), int(img.shape[1]), C.byref(dparams), T.ctypes, mr.ctypes, C.byref(rp), C.byref(n)),
+                 "DepthFrame")
+        return int(n.value)
+
+    def last_depth_cloud(self):
+        n = C.c_int64(0)
+        self._ck(self._L.fiesta_last_depth_cloud(self._h, None, C.c_int64(0), C.byref(n)), "last_depth_cloud")
+        out = np.empty((n.value, 3), np.float32)
+        if n.value:
+            self._ck(self._L.fiesta_last_depth_cloud(self._h, out.ctypes, n, C.byref(n)), "last_depth_cloud")
+        return out
 
     # --- state dumps / stats ---
     def export_distance(self):

@@ -199,3 +199,8 @@ cudaError_t fb_ray_frame(const FbGeom &g, const FbRayArgs &a, int nblocks_resolv
 int fb_ray_resolve_blocks(int device);
 cudaError_t fb_vis_point_cloud(const FbGeom &g, const double *occ, double l_occ, int zlo, int zhi, float *h_out, long long cap, long long *count, cudaStream_t s);
 cudaError_t fb_vis_slice(const FbGeom &g, const uint32_t *cobs, int slice, double max_dist, double *h_xyz, float *h_rgba, long long cap, long long *count, cudaStream_t s);
+struct FbDepthRel { double m[16]; };
+struct fiesta_depth_params;
+cudaError_t fb_depth_to_cloud(const uint16_t *d_img, const uint16_t *d_last, int rows, int cols, const fiesta_depth_params &p, int filter_on,
+                              const FbDepthRel &rel, float *d_pts, uint8_t *d_flags, uint32_t *d_sel, float *d_cloud, unsigned *d_count,
+                              void **tmp, size_t *tmp_bytes, unsigned *h_n, cudaStream_t s);

@@ -59,6 +59,9 @@ struct fiesta_map {
   double *d_qin, *d_qout; size_t cap_q;
   cudaEvent_t ev[4];
   unsigned long long *d_dbg;
+  // depth front end (next #1)
+  uint16_t *d_img[2]; size_t cap_img; unsigned image_cnt;
+  float *d_dpts, *d_dcloud; uint8_t *d_dflags; uint32_t *d_dsel; unsigned *d_dcount; void *d_dtmp; size_t d_dtmp_bytes; unsigned last_cloud_n;
   int mode;
   int shard_rank, shard_world, tile_x_lo, tile_x_hi;
   unsigned *d_halo_changed;
@@ -320,6 +323,7 @@ void fiesta_destroy(fiesta_map *m) {
   if (m->mode == FIESTA_MODE_EXACT) fb_exact_free(&m->X);
   if (m->d_dbg) cudaFree(m->d_dbg);
   if (m->d_halo_changed) cudaFree(m->d_halo_changed);
+  { void *q[] = {m->d_img[0], m->d_img[1], m->d_dpts, m->d_dcloud, m->d_dflags, m->d_dsel, m->d_dcount, m->d_dtmp}; for (void *x : q) if (x) cudaFree(x); }
   if (m->h_ctr) cudaFreeHost(m->h_ctr);
   if (m->h_ev) cudaFreeHost(m->h_ev);
   for (int i = 0; i < 4; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
@@ -574,6 +578,48 @@ int fiesta_raycast_frame(fiesta_map *m, const float *xyz, int64_t n, const doubl
   if ((r = ensure(&m->d_xyz, &m->cap_xyz, (size_t)n * 3, false, m->stream))) return r;
   if (n) CK(cudaMemcpyAsync(m->d_xyz, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, m->stream));
   return fiesta_raycast_frame_device(m, m->d_xyz, n, T, p);
+}
+
+int fiesta_depth_frame(fiesta_map *m, const uint16_t *depth, int rows, int cols, const fiesta_depth_params *dp, const double T[16],
+                       const double m_rel[16], const fiesta_raycast_params *rp, int64_t *n_points) {
+  if (!m || !depth || !dp || !T || !rp || rows <= 0 || cols <= 0) { set_error("fiesta_depth_frame: bad argument"); return FIESTA_ERR_INVALID; }
+  CK(cudaSetDevice(m->device));
+  const size_t N = (size_t)rows * cols;
+  if (N > m->cap_img) {
+    void *q[] = {m->d_img[0], m->d_img[1], m->d_dpts, m->d_dcloud, m->d_dflags, m->d_dsel};
+    for (void *x : q) if (x) cudaFree(x);
+    CK(cudaMalloc((void **)&m->d_img[0], N * 2)); CK(cudaMalloc((void **)&m->d_img[1], N * 2));
+    CK(cudaMalloc((void **)&m->d_dpts, N * 12)); CK(cudaMalloc((void **)&m->d_dcloud, N * 12));
+    CK(cudaMalloc((void **)&m->d_dflags, N)); CK(cudaMalloc((void **)&m->d_dsel, N * 4));
+    if (!m->d_dcount) CK(cudaMalloc((void **)&m->d_dcount, 16));
+    m->cap_img = N; m->image_cnt = 0;
+  }
+  ++m->image_cnt;                                                          // Fiesta.h:321-323: img_[image_cnt_ & 1] is the current image
+  uint16_t *cur = m->d_img[m->image_cnt & 1], *last = m->d_img[!(m->image_cnt & 1)];
+  CK(cudaMemcpyAsync(cur, depth, N * 2, cudaMemcpyHostToDevice, m->stream));
+  unsigned n = 0;
+  if (dp->use_depth_filter && m->image_cnt == 1) {                         // :353: the first image only primes the filter
+    m->last_cloud_n = 0;
+    if (n_points) *n_points = 0;
+    CK(cudaStreamSynchronize(m->stream));
+    return FIESTA_OK;
+  }
+  FbDepthRel rel;
+  for (int k = 0; k < 16; ++k) rel.m[k] = (dp->use_depth_filter && m_rel) ? m_rel[k] : (k % 5 == 0 ? 1.0 : 0.0);
+  CK(fb_depth_to_cloud(cur, last, rows, cols, *dp, dp->use_depth_filter ? 1 : 0, rel, m->d_dpts, m->d_dflags, m->d_dsel, m->d_dcloud, m->d_dcount,
+                       &m->d_dtmp, &m->d_dtmp_bytes, &n, m->stream));
+  m->st.kernel_launches += 3;
+  m->last_cloud_n = n;
+  if (n_points) *n_points = n;
+  if (n == 0) return FIESTA_OK;                                            // `if (cloud_.points.size() == 0) continue;` (Fiesta.h:430-433)
+  return fiesta_raycast_frame_device(m, m->d_dcloud, n, T, rp);
+}
+int fiesta_last_depth_cloud(fiesta_map *m, float *out, int64_t cap, int64_t *n_points) {
+  if (!m || !n_points) return FIESTA_ERR_INVALID;
+  *n_points = m->last_cloud_n;
+  const int64_t k = m->last_cloud_n < cap ? m->last_cloud_n : cap;
+  if (k > 0 && out) CK(cudaMemcpy(out, m->d_dcloud, (size_t)k * 12, cudaMemcpyDeviceToHost));
+  return FIESTA_OK;
 }
 
 int fiesta_check_update(fiesta_map *m) {

@@ -116,6 +116,21 @@ int fiesta_raycast_frame(fiesta_map *m, const float *xyz, int64_t n, const doubl
 int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, const double T[16],
                                 const fiesta_raycast_params *p);
 
+/* Fiesta::DepthConversion + RaycastMultithread in one call (Fiesta.h:319-382, then :281-303): `depth` is a HOST rows x cols
+ * uint16 image in millimetres (sensor_msgs::Image TYPE_16UC1, Fiesta.h:326-332).  Back-projection, the temporal depth filter
+ * against the previous image of this map and the pixel-order compaction run on the device; the cloud never leaves HBM.
+ * m_rel = last_transform_.inverse() * transform_ (row-major; only read when use_depth_filter != 0 and this is not the first
+ * image).  *n_points receives the size of the cloud that was ray cast (0 for the first filtered image, Fiesta.h:353). */
+typedef struct fiesta_depth_params {
+  double focal_x, focal_y, center_x, center_y;      /* parameters.h:139-140 */
+  int32_t use_depth_filter, depth_filter_margin;    /* parameters.h:143,145 */
+  double depth_filter_max_dist, depth_filter_min_dist, depth_filter_tolerance;
+} fiesta_depth_params;
+int fiesta_depth_frame(fiesta_map *m, const uint16_t *depth, int rows, int cols, const fiesta_depth_params *dp, const double T[16],
+                       const double m_rel[16], const fiesta_raycast_params *rp, int64_t *n_points);
+/* The cloud produced by the last fiesta_depth_frame (3 floats per point, pixel order), for inspection / parity tests. */
+int fiesta_last_depth_cloud(fiesta_map *m, float *out_xyz, int64_t cap, int64_t *n_points);
+
 /* ---- per-frame driver: Fiesta::UpdateEsdfEvent (Fiesta.h:507-514) ---- */
 /* bool ESDFMap::CheckUpdate() (ESDFMap.cpp:227-233): 1 if the occupancy queue is non-empty. */
 int fiesta_check_update(fiesta_map *m);

@@ -214,6 +214,25 @@ class OracleMap:
         return bool(self._f("check_consistency")(self._h))
 
 
+class DepthParams(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("use_filter", C.c_int), ("margin", C.c_int),
+                ("max_dist", C.c_double), ("min_dist", C.c_double), ("tolerance", C.c_double)]
+
+
+def depth_conversion(img, last, image_cnt, params, m_rel, kind=None):
+    """Restated Fiesta::DepthConversion (Fiesta.h:319-382): uint16 mm image -> (n,3) float32 cloud in pixel order."""
+    kind = kind or best_kind()
+    f = getattr(_lib(kind), _PREFIX[kind] + "depth_conversion")
+    f.restype = C.c_long
+    img = np.ascontiguousarray(img, np.uint16)
+    rows, cols = img.shape
+    last = np.ascontiguousarray(last if last is not None else img, np.uint16)
+    out = np.empty((rows * cols, 3), np.float32)
+    mr = np.ascontiguousarray(m_rel if m_rel is not None else np.eye(4), np.float64).reshape(16)
+    n = int(f(img.ctypes, last.ctypes, rows, cols, C.c_uint(image_cnt), C.byref(params), mr.ctypes, out.ctypes))
+    return out[:n].copy()
+
+
 def raycast(start, end, mn, mx, kind=None):
     """Reference Raycast() (raycast.cpp:56-158): list of integer voxel coordinates, or None if it threw."""
     kind = kind or best_kind()

@@ -21,6 +21,7 @@
 #include "ESDFMap.h"
 #undef private
 #include "raycast.h"
+#include "depth_restated.h"
 
 namespace {
 
@@ -249,6 +250,11 @@ long fiesta_ref_get_slice_marker(void *h, int slice, double max_dist, double *xy
     rgba[4 * i] = mk.colors[i].r; rgba[4 * i + 1] = mk.colors[i].g; rgba[4 * i + 2] = mk.colors[i].b; rgba[4 * i + 3] = mk.colors[i].a;
   }
   return n;
+}
+
+long fiesta_ref_depth_conversion(const uint16_t *img, const uint16_t *last, int rows, int cols, unsigned image_cnt,
+                                 const oracle_depth_params *p, const double *m_rel, float *cloud) {
+  return oracle_depth_conversion(img, last, rows, cols, image_cnt, p, m_rel, cloud);
 }
 
 int fiesta_ref_check_consistency(void *h) {

@@ -121,6 +121,19 @@ def depth_frame(scene, p, yaw, width=640, height=480, scale=1.0, max_depth=10.0)
     return pts, T
 
 
+def depth_image(scene, p, yaw, width=640, height=480, scale=1.0):
+    """uint16 millimetre depth image (sensor_msgs::Image TYPE_16UC1) of the scene + the camera transform_."""
+    fx, fy, cx, cy = FX * scale, FY * scale, CX * scale, CY * scale
+    u, v = np.meshgrid(np.arange(width), np.arange(height))
+    d_cam = np.stack([(u - cx) / fx, (v - cy) / fy, np.ones_like(u, float)], -1).reshape(-1, 3)
+    T = camera_transform(p, yaw)
+    d_w = d_cam @ T[:3, :3].T
+    nrm = np.linalg.norm(d_w, axis=1)
+    t = scene.ranges(np.asarray(p, float), d_w / nrm[:, None])
+    mm = np.clip(np.round(t / nrm * 1000.0), 0, 65535).astype(np.uint16)
+    return mm.reshape(height, width), T
+
+
 def lidar_frame(scene, p, yaw, beams=64, azimuths=1563, noise_seed=None):
     """64 beams, elevation uniformly spaced in [-15, +15] deg, x 1563 azimuths = 100 032 points."""
     el = np.deg2rad(np.linspace(-15.0, 15.0, beams))
