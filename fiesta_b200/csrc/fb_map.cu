@@ -588,6 +588,7 @@ int fiesta_depth_frame(fiesta_map *m, const uint16_t *depth, int rows, int cols,
   if (N > m->cap_img) {
     void *q[] = {m->d_img[0], m->d_img[1], m->d_dpts, m->d_dcloud, m->d_dflags, m->d_dsel};
     for (void *x : q) if (x) cudaFree(x);
+    m->d_img[0] = m->d_img[1] = nullptr; m->d_dpts = m->d_dcloud = nullptr; m->d_dflags = nullptr; m->d_dsel = nullptr; m->cap_img = 0;
     CK(cudaMalloc((void **)&m->d_img[0], N * 2)); CK(cudaMalloc((void **)&m->d_img[1], N * 2));
     CK(cudaMalloc((void **)&m->d_dpts, N * 12)); CK(cudaMalloc((void **)&m->d_dcloud, N * 12));
     CK(cudaMalloc((void **)&m->d_dflags, N)); CK(cudaMalloc((void **)&m->d_dsel, N * 4));
@@ -830,19 +831,23 @@ static int run_export(fiesta_map *m, double *dist, int *cobs3, double *occ, int 
   CK(cudaSetDevice(m->device));
   const size_t G = (size_t)m->g.total;
   double *dd = nullptr, *dof = nullptr; int *dc = nullptr, *dh = nullptr, *dt = nullptr;
-  if (dist) CK(cudaMalloc((void **)&dd, G * 8));
-  if (occ) CK(cudaMalloc((void **)&dof, G * 8));
-  if (cobs3) CK(cudaMalloc((void **)&dc, G * 12));
-  if (hit) { CK(cudaMalloc((void **)&dh, G * 4)); CK(cudaMalloc((void **)&dt, G * 4)); }
-  k_export<<<(unsigned)((G + 255) / 256), 256, 0, m->stream>>>(m->g, m->cobs, m->occ, m->cnt, dd, dc, dof, dh, dt);
-  m->st.kernel_launches++;
-  CK(cudaGetLastError());
-  if (dist) CK(cudaMemcpyAsync(dist, dd, G * 8, cudaMemcpyDeviceToHost, m->stream));
-  if (occ) CK(cudaMemcpyAsync(occ, dof, G * 8, cudaMemcpyDeviceToHost, m->stream));
-  if (cobs3) CK(cudaMemcpyAsync(cobs3, dc, G * 12, cudaMemcpyDeviceToHost, m->stream));
-  if (hit) { CK(cudaMemcpyAsync(hit, dh, G * 4, cudaMemcpyDeviceToHost, m->stream)); CK(cudaMemcpyAsync(tot, dt, G * 4, cudaMemcpyDeviceToHost, m->stream)); }
-  CK(cudaStreamSynchronize(m->stream));
+  cudaError_t e = cudaSuccess;
+  if (dist) e = cudaMalloc((void **)&dd, G * 8);
+  if (!e && occ) e = cudaMalloc((void **)&dof, G * 8);
+  if (!e && cobs3) e = cudaMalloc((void **)&dc, G * 12);
+  if (!e && hit) { e = cudaMalloc((void **)&dh, G * 4); if (!e) e = cudaMalloc((void **)&dt, G * 4); }
+  if (!e) {
+    k_export<<<(unsigned)((G + 255) / 256), 256, 0, m->stream>>>(m->g, m->cobs, m->occ, m->cnt, dd, dc, dof, dh, dt);
+    m->st.kernel_launches++;
+    e = cudaGetLastError();
+  }
+  if (!e && dist) e = cudaMemcpyAsync(dist, dd, G * 8, cudaMemcpyDeviceToHost, m->stream);
+  if (!e && occ) e = cudaMemcpyAsync(occ, dof, G * 8, cudaMemcpyDeviceToHost, m->stream);
+  if (!e && cobs3) e = cudaMemcpyAsync(cobs3, dc, G * 12, cudaMemcpyDeviceToHost, m->stream);
+  if (!e && hit) { e = cudaMemcpyAsync(hit, dh, G * 4, cudaMemcpyDeviceToHost, m->stream); if (!e) e = cudaMemcpyAsync(tot, dt, G * 4, cudaMemcpyDeviceToHost, m->stream); }
+  if (!e) e = cudaStreamSynchronize(m->stream);
   cudaFree(dd); cudaFree(dof); cudaFree(dc); cudaFree(dh); cudaFree(dt);
+  if (e != cudaSuccess) { set_error("export failed: %s", cudaGetErrorString(e)); return FIESTA_ERR_CUDA; }
   return FIESTA_OK;
 }
 int fiesta_export_distance(fiesta_map *m, double *out) { return (!m || !out) ? FIESTA_ERR_INVALID : run_export(m, out, nullptr, nullptr, nullptr, nullptr); }
