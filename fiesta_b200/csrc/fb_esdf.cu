@@ -271,7 +271,7 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
               const uint32_t c = wn & FB_CODE_MASK;
               // candidate iff the neighbour has a closest obstacle (ESDFMap.cpp:353) and either it is in the queue (its
               // push phase, :375-391) or this voxel is (its pull phase, :349-367)
-              if (c >= 2u && ((nmask[h] >> k) & 1u) && ((wn >> 31) | fresh[h])) {
+              if (c >= 2u && c != best && ((nmask[h] >> k) & 1u) && ((wn >> 31) | fresh[h])) {   // c == best cannot improve (same obstacle)
                 int ox, oy, oz; fb_unpack(c, ox, oy, oz); ox -= vx; oy -= vy; oz -= vz;
                 const unsigned d = (unsigned)(ox * ox + oy * oy + oz * oz);
                 if (d < bestd || (d == bestd && c < best)) { bestd = d; best = c; }   // strict improvement; ties -> smallest coordinate

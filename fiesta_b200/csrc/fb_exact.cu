@@ -98,6 +98,69 @@ __device__ __forceinline__ XState x_state(const FbGeom &g, const uint32_t *cobs,
   return s;
 }
 
+
+// ---- per-voxel offer summaries ------------------------------------------------------------------------------------
+// Every voxel that some element of the generation can write (its 24 neighbours and itself) is a TARGET.  Once per round a
+// target's <= 25 offers are gathered into a summary {first = earliest timestamp of an offer that beats the snapshot,
+// best = lexicographic minimum (distance, timestamp) over all offers}.  A reader at time T then gets the snapshot if
+// T <= first, `best` if T > best.ts, and has to gather the offers itself only in between (about 1 % of the queries in the
+// CPU model, oracle/exact_model.c); non-targets have no writer and read as the snapshot.
+__device__ __forceinline__ uint4 x_summarize(const FbGeom &g, const uint32_t *cobs, const unsigned long long *MB, int x, int y, int z) {
+  const XState f = x_state(g, cobs, MB, x, y, z, XNONE);
+  unsigned first = XNONE;
+  const long long v = fb_ii(g, x, y, z);
+  const uint32_t c0 = cobs[v] & FB_CODE_MASK;
+  if (c0 != FB_UNKNOWN && fb_in_range(g, x, y, z)) {
+    const unsigned d0 = x_dist_of(x, y, z, c0);
+#pragma unroll 8
+    for (int k = 0; k < 24; ++k) {
+      const int qx = x - x_dirs[k][0], qy = y - x_dirs[k][1], qz = z - x_dirs[k][2];
+      if (!fb_in_grid(g, qx, qy, qz)) continue;
+      const unsigned long long w = MB[fb_ii(g, qx, qy, qz)];
+      if (w == XMB_NONE || x_mb_kind(w) != X_PUSH) continue;
+      const unsigned ts = x_mb_idx(w) * 32u + (unsigned)k;
+      if (ts < first && x_d2(x, y, z, x_mb_code(w)) < d0) first = ts;
+    }
+    const unsigned long long w = MB[v];
+    if (w != XMB_NONE && x_mb_kind(w) == X_PULL) {
+      const unsigned ts = x_mb_idx(w) * 32u + 24u;
+      if (ts < first && x_d2(x, y, z, x_mb_code(w)) < d0) first = ts;
+    }
+  }
+  return make_uint4(first, f.d, f.ts, f.c);
+}
+__device__ __forceinline__ XState x_state_sum(const FbGeom &g, const uint32_t *cobs, const unsigned long long *MB, const uint4 *SUM,
+                                              const uint32_t *SUMg, unsigned gen, int x, int y, int z, unsigned T) {
+  const long long v = fb_ii(g, x, y, z);
+  XState s;
+  bool snapshot = SUMg[v] != gen;
+  uint4 u = make_uint4(0, 0, 0, 0);
+  if (!snapshot) { u = SUM[v]; snapshot = u.x == XNONE || T <= u.x; }
+  if (snapshot) { s.c = cobs[v] & FB_CODE_MASK; s.d = x_dist_of(x, y, z, s.c); s.ts = XNONE; return s; }
+  if (T > u.z) { s.d = u.y; s.ts = u.z; s.c = u.w; return s; }
+  return x_state(g, cobs, MB, x, y, z, T);                    // first < T <= best.ts: gather
+}
+// Targets of the generation (deduplicated through SUMg).
+__global__ void k_x_targets(FbGeom g, const uint32_t *E, unsigned n, uint32_t *SUMg, unsigned gen, uint32_t *targets, unsigned *ntargets) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int x, y, z; x_coords(g, E[i], x, y, z);
+  for (int k = 0; k < 25; ++k) {
+    const int nx = k < 24 ? x + x_dirs[k][0] : x, ny = k < 24 ? y + x_dirs[k][1] : y, nz = k < 24 ? z + x_dirs[k][2] : z;
+    if (!fb_in_range(g, nx, ny, nz) || !fb_in_grid(g, nx, ny, nz)) continue;
+    const long long v = fb_ii(g, nx, ny, nz);
+    if (SUMg[v] != gen && atomicExch(&SUMg[v], gen) != gen) targets[atomicAdd(ntargets, 1u)] = (uint32_t)v;
+  }
+}
+__global__ void k_x_sum(FbGeom g, const uint32_t *targets, unsigned nt, const uint32_t *cobs, const unsigned long long *MB, uint4 *SUM,
+                        const uint32_t *tdirty, unsigned stamp, int first_round) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nt) return;
+  int x, y, z; x_coords(g, targets[i], x, y, z);
+  if (!first_round && tdirty[((x >> 3) * g.ty + (y >> 3)) * g.tz + (z >> 3)] != stamp) return;
+  SUM[targets[i]] = x_summarize(g, cobs, MB, x, y, z);
+}
+
 // ------------------------------------------------------------------ occupancy (ordered)
 __global__ void k_x_gather_keys(const uint32_t *vox, unsigned n, const unsigned long long *tkey, unsigned long long *keys) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,8 +294,8 @@ __global__ void k_x_init_beh(const uint32_t *E, unsigned n, const uint32_t *cobs
 // new behaviour of earlier ones); an element is re-evaluated only in the first round of a generation or when an element
 // within reach (<= 4 voxels: its own 8^3 tile or one of the 26 around it) changed its behaviour in the previous round.
 // The loop ends with a round in which nothing changed, which reads a stable B: that state is the sequential execution.
-__global__ void k_x_eval(FbGeom g, const uint32_t *E, unsigned n, const uint32_t *cobs, unsigned long long *MB, uint32_t *tdirty,
-                         unsigned stamp, int first_round, unsigned *changed) {
+__global__ void k_x_eval(FbGeom g, const uint32_t *E, unsigned n, const uint32_t *cobs, unsigned long long *MB, const uint4 *SUM,
+                         const uint32_t *SUMg, unsigned gen, uint32_t *tdirty, unsigned stamp, int first_round, unsigned *changed) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t p = E[i];
@@ -240,7 +303,7 @@ __global__ void k_x_eval(FbGeom g, const uint32_t *E, unsigned n, const uint32_t
   const int tx = x >> 3, ty = y >> 3, tz = z >> 3;
   if (!first_round && tdirty[(tx * g.ty + ty) * g.tz + tz] != stamp) return;
   const unsigned T0 = i * 32u;
-  const XState s = x_state(g, cobs, MB, x, y, z, T0);
+  const XState s = x_state_sum(g, cobs, MB, SUM, SUMg, gen, x, y, z, T0);
   const uint32_t c0 = cobs[p] & FB_CODE_MASK;
   unsigned long long nb;
   if (s.d != x_dist_of(x, y, z, c0)) nb = x_mb(i, X_DEAD, 0);  // `xx.distance_ != distance_buffer_[idx]`: stale (:345)
@@ -249,7 +312,7 @@ __global__ void k_x_eval(FbGeom g, const uint32_t *E, unsigned n, const uint32_t
     for (int k = 0; k < 24; ++k) {                             // pull phase (:349-367)
       const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
       if (!fb_in_range(g, nx, ny, nz) || !fb_in_grid(g, nx, ny, nz)) continue;
-      const XState sn = x_state(g, cobs, MB, nx, ny, nz, T0);
+      const XState sn = x_state_sum(g, cobs, MB, SUM, SUMg, gen, nx, ny, nz, T0);
       if (sn.c < 2u) continue;
       const unsigned t = x_d2(x, y, z, sn.c);
       if (curd > t) { curd = t; curc = sn.c; ch = true; }
@@ -278,7 +341,7 @@ __global__ void k_x_collect(FbGeom g, const uint32_t *E, unsigned n, const uint3
   if (on) work[slot] = i;
 }
 __global__ void k_x_eval_warp(FbGeom g, const uint32_t *E, const uint32_t *work, const unsigned *nwork, const uint32_t *cobs, unsigned long long *MB,
-                              uint32_t *tdirty, unsigned stamp, unsigned *changed) {
+                              const uint4 *SUM, const uint32_t *SUMg, unsigned gen, uint32_t *tdirty, unsigned stamp, unsigned *changed) {
   const unsigned lane = threadIdx.x & 31u, nw = *nwork;
   for (unsigned wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < nw; wi += (gridDim.x * blockDim.x) >> 5) {
   const unsigned i = work[wi];
@@ -290,7 +353,7 @@ __global__ void k_x_eval_warp(FbGeom g, const uint32_t *E, const uint32_t *work,
   bool valid = lane == 24;
   if (lane < 24) { qx += x_dirs[lane][0]; qy += x_dirs[lane][1]; qz += x_dirs[lane][2]; valid = fb_in_range(g, qx, qy, qz) && fb_in_grid(g, qx, qy, qz); }
   XState st; st.d = 0xffffffffu; st.c = 0; st.ts = XNONE;
-  if (valid) st = x_state(g, cobs, MB, qx, qy, qz, T0);      // lanes 0..23: neighbour k at pop time; lane 24: the element itself
+  if (valid) st = x_state_sum(g, cobs, MB, SUM, SUMg, gen, qx, qy, qz, T0);   // lanes 0..23: neighbour k at pop time; lane 24: the element itself
   const unsigned sd = __shfl_sync(0xffffffffu, st.d, 24);
   const uint32_t sc = __shfl_sync(0xffffffffu, st.c, 24);
   const uint32_t c0 = cobs[p] & FB_CODE_MASK;
@@ -318,7 +381,7 @@ __global__ void k_x_eval_warp(FbGeom g, const uint32_t *E, const uint32_t *work,
   }
 }
 // Final writes of the generation -> slots (timestamp order) of the next generation's queue.
-__global__ void k_x_commit(FbGeom g, const uint32_t *E, unsigned n, const uint32_t *cobs, const unsigned long long *MB,
+__global__ void k_x_commit(FbGeom g, const uint32_t *E, unsigned n, const unsigned long long *MB, const uint4 *SUM, const uint32_t *SUMg, unsigned gen,
                            uint32_t *slotv, uint32_t *slotc, uint8_t *slotf, unsigned long long *expansions) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long b = XMB_NONE;
@@ -328,18 +391,21 @@ __global__ void k_x_commit(FbGeom g, const uint32_t *E, unsigned n, const uint32
   if ((threadIdx.x & 31) == 0 && nlive) atomicAdd(expansions, (unsigned long long)nlive);   // `times++` (:347)
   if (!live) return;
   int x, y, z; x_coords(g, E[i], x, y, z);
+  // The last accepted write to a voxel is its summary's `best`; the element/direction that made it owns the slot.
   if (x_mb_kind(b) == X_PUSH) {
     for (int k = 0; k < 24; ++k) {                             // push phase (:375-391)
       const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
       if (!fb_in_range(g, nx, ny, nz) || !fb_in_grid(g, nx, ny, nz)) continue;
-      const XState f = x_state(g, cobs, MB, nx, ny, nz, XNONE);
+      const long long v = fb_ii(g, nx, ny, nz);
       const unsigned ts = i * 32u + (unsigned)k;
-      if (f.ts == ts) { slotv[ts] = (uint32_t)fb_ii(g, nx, ny, nz); slotc[ts] = f.c; slotf[ts] = 1; }
+      if (SUMg[v] != gen) continue;
+      const uint4 u = SUM[v];
+      if (u.z == ts) { slotv[ts] = (uint32_t)v; slotc[ts] = u.w; slotf[ts] = 1; }
     }
   } else {
-    const XState f = x_state(g, cobs, MB, x, y, z, XNONE);
     const unsigned ts = i * 32u + 24u;
-    if (f.ts == ts) { slotv[ts] = E[i]; slotc[ts] = f.c; slotf[ts] = 1; }
+    const uint4 u = SUM[E[i]];
+    if (SUMg[E[i]] == gen && u.z == ts) { slotv[ts] = E[i]; slotc[ts] = u.w; slotf[ts] = 1; }
   }
 }
 __global__ void k_x_clear_M(const uint32_t *E, unsigned n, unsigned long long *MB) {
@@ -416,6 +482,7 @@ cudaError_t fb_exact_init(FbExact *X, const FbGeom &g, cudaStream_t s) {
   const size_t P = (size_t)g.ptotal;
   XCK(cudaMalloc((void **)&X->MB, P * 8)); XCK(cudaMalloc((void **)&X->LS, P * 8)); XCK(cudaMalloc((void **)&X->tkey, P * 8));
   XCK(cudaMalloc((void **)&X->touched, P * 4));
+  XCK(cudaMalloc((void **)&X->SUM, P * 16)); XCK(cudaMalloc((void **)&X->SUMg, P * 4)); XCK(cudaMemsetAsync(X->SUMg, 0, P * 4, s));
   XCK(cudaMalloc((void **)&X->tdirty, (size_t)g.ntiles * 4)); XCK(cudaMemsetAsync(X->tdirty, 0, (size_t)g.ntiles * 4, s));
   XCK(cudaMalloc((void **)&X->d_count, 16)); XCK(cudaMalloc((void **)&X->d_flag, 16));
   XCK(cudaMallocHost((void **)&X->h_count, 16));
@@ -423,11 +490,11 @@ cudaError_t fb_exact_init(FbExact *X, const FbGeom &g, cudaStream_t s) {
   k_x_fill64<<<148 * 8, 256, 0, s>>>(X->MB, P, XMB_NONE);
   k_x_fill64<<<148 * 8, 256, 0, s>>>(X->tkey, P, ~0ull);
   XCK(cudaMemsetAsync(X->LS, 0, P * 8, s));
-  X->tclock = 1; X->key_base = 0; X->eval_clock = 1;
+  X->tclock = 1; X->key_base = 0; X->eval_clock = 1; X->gen_id = 0;
   return cudaGetLastError();
 }
 void fb_exact_free(FbExact *X) {
-  void *p[] = {X->MB, X->LS, X->tkey, X->touched, X->tdirty, X->d_count, X->d_flag, X->E[0], X->E[1], X->slotv, X->slotc, X->slotf, X->sel,
+  void *p[] = {X->MB, X->LS, X->tkey, X->touched, X->tdirty, X->SUM, X->SUMg, X->targets, X->work, X->d_count, X->d_flag, X->E[0], X->E[1], X->slotv, X->slotc, X->slotf, X->sel,
                X->k1, X->k2, X->k1b, X->k2b, X->dv, X->idx[0], X->idx[1], X->deps, X->nc[0], X->nc[1], X->flags, X->flags2, X->cub_tmp};
   for (void *q : p) if (q) cudaFree(q);
   if (X->h_count) cudaFreeHost(X->h_count);
@@ -562,7 +629,8 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
   static const bool xdbg = getenv("FIESTA_DEBUG_X") != nullptr;
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-  double t_eval = 0, t_commit = 0, t_select = 0, t_apply = 0; auto t_start = now();
+  double t_eval = 0, t_commit = 0, t_select = 0, t_apply = 0, t_k[5] = {0, 0, 0, 0, 0}; auto t_start = now();
+  auto lap = [&](int k, std::chrono::steady_clock::time_point &a) { if (xdbg) { cudaStreamSynchronize(s); auto b = now(); t_k[k] += ms(a, b); a = b; } };
   int cur = 0;
   XCK(cudaMemsetAsync(X->d_count + 2, 0, 8, s));               // expansions counter (u64 at d_count[2..3])
   while (nE) {
@@ -575,19 +643,36 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
     if ((e = x_ensure(X, &X->sel, &X->cap_sel, nslots))) return e;
     auto t0 = now();
     k_x_init_beh<<<nblk(nE), 256, 0, s>>>(X->E[cur], nE, cobs, X->MB);
+    // targets of this generation
+    ++X->gen_id;
+    if ((e = x_ensure(X, &X->targets, &X->cap_targets, (size_t)nE * 25))) return e;
+    if ((e = x_ensure(X, &X->work, &X->cap_work, (size_t)nE))) return e;
+    XCK(cudaMemsetAsync(X->d_count, 0, 4, s));
+    auto tl = now();
+    k_x_targets<<<nblk(nE), 256, 0, s>>>(g, X->E[cur], nE, X->SUMg, X->gen_id, X->targets, X->d_count);
+    XCK(cudaMemcpyAsync(X->h_count, X->d_count, 4, cudaMemcpyDeviceToHost, s));
+    XCK(cudaStreamSynchronize(s));
+    const unsigned nT = *X->h_count;
+    *launches += 2;
+    lap(0, tl);
     // Rounds are launched four at a time between host checks: a round after convergence finds no dirty tile and costs
     // next to nothing, and a batch that changed nothing proves that the last state survived a full round.
     for (int it = 0; it < 100000; it += 4) {
       for (int q = 0; q < 4; ++q) {
         ++X->eval_clock;
-        if (it + q == 0) k_x_eval<<<nblk(nE, 128), 128, 0, s>>>(g, X->E[cur], nE, cobs, X->MB, X->tdirty, X->eval_clock, 1, X->d_flag);
+        const int first = it + q == 0;
+        k_x_sum<<<nblk(nT), 256, 0, s>>>(g, X->targets, nT, cobs, X->MB, X->SUM, X->tdirty, X->eval_clock, first);
+        lap(1, tl);
+        if (first) { k_x_eval<<<nblk(nE, 128), 128, 0, s>>>(g, X->E[cur], nE, cobs, X->MB, X->SUM, X->SUMg, X->gen_id, X->tdirty, X->eval_clock, 1, X->d_flag); lap(2, tl); }
         else {
           XCK(cudaMemsetAsync(X->d_count + 1, 0, 4, s));
-          k_x_collect<<<nblk(nE), 256, 0, s>>>(g, X->E[cur], nE, X->tdirty, X->eval_clock, X->sel, X->d_count + 1);
-          k_x_eval_warp<<<148 * 4, 256, 0, s>>>(g, X->E[cur], X->sel, X->d_count + 1, cobs, X->MB, X->tdirty, X->eval_clock, X->d_flag);
+          k_x_collect<<<nblk(nE), 256, 0, s>>>(g, X->E[cur], nE, X->tdirty, X->eval_clock, X->work, X->d_count + 1);
+          lap(3, tl);
+          k_x_eval_warp<<<148 * 4, 256, 0, s>>>(g, X->E[cur], X->work, X->d_count + 1, cobs, X->MB, X->SUM, X->SUMg, X->gen_id, X->tdirty, X->eval_clock, X->d_flag);
+          lap(4, tl);
         }
       }
-      *launches += 4;
+      *launches += 10;
       unsigned ch = 0;
       if ((e = x_flag(X, s, &ch))) return e;
       st->eval_rounds += 4;
@@ -595,7 +680,7 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
     }
     auto t1 = now();
     XCK(cudaMemsetAsync(X->slotf, 0, nslots, s));
-    k_x_commit<<<nblk(nE, 128), 128, 0, s>>>(g, X->E[cur], nE, cobs, X->MB, X->slotv, X->slotc, X->slotf, (unsigned long long *)(X->d_count + 2));
+    k_x_commit<<<nblk(nE, 128), 128, 0, s>>>(g, X->E[cur], nE, X->MB, X->SUM, X->SUMg, X->gen_id, X->slotv, X->slotc, X->slotf, (unsigned long long *)(X->d_count + 2));
     k_x_clear_M<<<nblk(nE), 256, 0, s>>>(X->E[cur], nE, X->MB);
     if (xdbg) cudaStreamSynchronize(s);
     auto t2 = now();
@@ -625,6 +710,6 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
   XCK(cudaMemcpyAsync(X->h_count, X->d_count + 2, 8, cudaMemcpyDeviceToHost, s));
   XCK(cudaStreamSynchronize(s));
   st->expansions = *(unsigned long long *)X->h_count;
-  if (xdbg) fprintf(stderr, "[x] gens %u rounds %u deps %u | relax %.1f ms: eval %.1f commit %.1f select %.1f apply %.1f\n", st->generations, st->eval_rounds, st->dependants, ms(t_start, now()), t_eval, t_commit, t_select, t_apply);
+  if (xdbg) fprintf(stderr, "[x] gens %u rounds %u deps %u | relax %.1f ms: eval %.1f (targets %.1f sum %.1f eval1 %.1f collect %.1f evalw %.1f) commit %.1f select %.1f apply %.1f\n", st->generations, st->eval_rounds, st->dependants, ms(t_start, now()), t_eval, t_k[0], t_k[1], t_k[2], t_k[3], t_k[4], t_commit, t_select, t_apply);
   return cudaSuccess;
 }

@@ -16,6 +16,10 @@ struct FbExact {
   unsigned long long tclock;   // relink clock
   unsigned long long key_base; // observation clock
   unsigned *d_count, *d_flag, *h_count;
+  uint4 *SUM;                  // per voxel offer summary of the current generation: {first ts, best d, best ts, best code}
+  uint32_t *SUMg;              // per voxel: generation id for which SUM is valid (= the voxel is a push/pull target)
+  unsigned gen_id;
+  uint32_t *targets, *work; size_t cap_targets, cap_work;
   uint32_t *tdirty;            // per 8^3 tile: evaluation round in which its elements must be re-evaluated
   unsigned eval_clock;
   uint32_t *E[2]; size_t cap_E[2];
