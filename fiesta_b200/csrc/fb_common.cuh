@@ -128,19 +128,19 @@ struct FbTouch {
 // integration (num_miss_ == 1) queues the voxel -- fast mode: marks its 8^3 tile; exact mode: lists the voxel and keeps
 // the serial time `key` of its earliest observation (= its position in occupancy_queue_).
 __device__ __forceinline__ void fb_touch(const FbGeom &g, const FbTouch &t, unsigned ii, unsigned occ, unsigned long long key) {
-  const unsigned long long old = atomicAdd(&t.cnt[ii], ((unsigned long long)occ << 32) | 1ull);
-  const bool first = (unsigned)(old & 0xffffffffull) == 0u;
   if (t.tkey) {
+    const unsigned long long old = atomicAdd(&t.cnt[ii], ((unsigned long long)occ << 32) | 1ull);
     atomicMin(&t.tkey[ii], key);
-    if (first) t.xtouched[atomicAdd(&t.ctr->n_xtouched, 1u)] = ii;
+    if ((unsigned)(old & 0xffffffffull) == 0u) t.xtouched[atomicAdd(&t.ctr->n_xtouched, 1u)] = ii;
     return;
   }
-  if (first) {
-    const unsigned z = ii % (unsigned)g.pz, xy = ii / (unsigned)g.pz, y = xy % (unsigned)g.gy, x = xy / (unsigned)g.gy;
-    const unsigned tile = ((x >> 3) * g.ty + (y >> 3)) * g.tz + (z >> 3);
-    if (__ldcg(&t.touch_flag[tile]) != t.epoch && atomicExch(&t.touch_flag[tile], t.epoch) != t.epoch)
-      t.touch_list[atomicAdd(&t.ctr->n_touch_tiles, 1u)] = tile;
-  }
+  // Fast mode: the tile is queued when it holds any pending observation, which is the same set as "some voxel of it saw its
+  // first observation" -- so the counter update needs no return value (a fire-and-forget RED instead of a round trip).
+  atomicAdd(&t.cnt[ii], ((unsigned long long)occ << 32) | 1ull);
+  const unsigned z = ii % (unsigned)g.pz, xy = ii / (unsigned)g.pz, y = xy % (unsigned)g.gy, x = xy / (unsigned)g.gy;
+  const unsigned tile = ((x >> 3) * g.ty + (y >> 3)) * g.tz + (z >> 3);
+  if (__ldcg(&t.touch_flag[tile]) != t.epoch && atomicExch(&t.touch_flag[tile], t.epoch) != t.epoch)
+    t.touch_list[atomicAdd(&t.ctr->n_touch_tiles, 1u)] = tile;
 }
 #endif
 
@@ -186,6 +186,7 @@ struct FbRayArgs {
   unsigned owner_tag;     // endpoint-owner frame tag
   unsigned max_rounds;
   FbCounters *ctr;
+  unsigned long long *dbg;  // FIESTA_DEBUG_RAY: per-round {work, check ns, walk ns}
 };
 
 cudaError_t fb_esdf_make_tensor_map(CUtensorMap *out, const FbGeom &g, uint32_t *cobs, char *err, int errlen);

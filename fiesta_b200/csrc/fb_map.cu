@@ -543,11 +543,11 @@ int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, co
     size_t c1 = m->cap_rays, c2 = m->cap_rays, c3 = m->cap_rays, c4 = m->cap_rays;
     if ((r = ensure(&m->ray_len, &c1, need_rays, false, m->stream))) return r;
     if ((r = ensure(&m->ray_reach, &c2, need_rays, false, m->stream))) return r;
-    if ((r = ensure(&m->ray_act, &c3, need_rays, false, m->stream))) return r;
+    if ((r = ensure(&m->ray_act, &c3, 2 * need_rays, false, m->stream))) return r;
     if ((r = ensure(&m->ray_dirty, &c4, need_rays, false, m->stream))) return r;
     m->cap_rays = c1;
     if (c2 < m->cap_rays) m->cap_rays = c2;
-    if (c3 < m->cap_rays) m->cap_rays = c3;
+    if (c3 / 2 < m->cap_rays) m->cap_rays = c3 / 2;
     if (c4 < m->cap_rays) m->cap_rays = c4;
   }
   if ((r = ensure(&m->ray_list, &m->cap_ray_list, (size_t)a.cap * (size_t)n, false, m->stream))) return r;
@@ -556,6 +556,9 @@ int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, co
   a.tkey = m->mode == FIESTA_MODE_EXACT ? m->X.tkey : nullptr; a.xtouched = m->X.touched; a.key_base = m->X.key_base;
   m->X.key_base += 1ull << 30;
   a.ray_list = m->ray_list; a.ray_len = m->ray_len; a.ray_reach = m->ray_reach; a.ray_act = m->ray_act; a.ray_dirty = m->ray_dirty; a.ctr = m->d_ctr;
+  static const bool dbg_ray = getenv("FIESTA_DEBUG_RAY") != nullptr;
+  a.dbg = nullptr;
+  if (dbg_ray) { if (!m->d_dbg) CK(cudaMalloc((void **)&m->d_dbg, 1024 * 8)); CK(cudaMemsetAsync(m->d_dbg, 0, 1024 * 8, m->stream)); a.dbg = m->d_dbg; }
   CK(cudaEventRecord(m->ev[0], m->stream));
   k_reset_ray_ctr<<<1, 1, 0, m->stream>>>(m->d_ctr);
   int launches = 1;
@@ -567,6 +570,13 @@ int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, co
   m->st.rays_cast = m->h_ctr->rays_cast; m->st.rays_dropped = m->h_ctr->rays_dropped;
   m->st.ray_voxels = (int64_t)m->h_ctr->ray_voxels; m->st.raycast_rounds = m->h_ctr->ray_rounds;
   m->st.touched_voxels = (int64_t)m->n_touch_tiles * 512;
+  if (a.dbg) {
+    unsigned long long h[1024];
+    CK(cudaMemcpy(h, m->d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[ray] rounds=%u counts %.0fus", m->h_ctr->ray_rounds, h[0] * 1e-3);
+    for (unsigned r2 = 1; r2 < m->h_ctr->ray_rounds && r2 < 300; ++r2) fprintf(stderr, " | %llu %.0f+%.0fus", h[3 * r2], h[3 * r2 + 1] * 1e-3, h[3 * r2 + 2] * 1e-3);
+    fprintf(stderr, "\n");
+  }
   if (m->h_ctr->ray_error == 3) { set_error("fiesta_raycast_frame: stamp resolution did not converge"); return FIESTA_ERR_LIMIT; }
   return FIESTA_OK;
 }

@@ -221,6 +221,7 @@ __global__ void k_ray_trace(FbGeom g, FbRayArgs a) {
 // One warp per ray.  reach[i] = index at which the back-walk stops (L if it runs off the list) | FB_REACH_BLOCKED when it
 // stopped at a voxel stamped by an earlier ray (that voxel is still counted, Fiesta.h:248-268).
 #define FB_REACH_BLOCKED 0x40000000
+#define FB_RAY_CLEAN 0xffffffffu
 
 // Is the voxel whose claim word is `seen` validly claimed by a ray with a lower index than `i`?
 __device__ __forceinline__ bool fb_claim_blocks(const FbRayArgs &a, unsigned seen, unsigned i) {
@@ -231,34 +232,39 @@ __device__ __forceinline__ bool fb_claim_blocks(const FbRayArgs &a, unsigned see
 
 // One warp walks ray i from the far end: stops at the first voxel validly claimed by a lower ray (or at the
 // min_ray_length class), claims what it passes and marks every higher ray it displaces dirty.  Returns the new reach.
-__device__ __forceinline__ int fb_walk_ray(const FbRayArgs &a, unsigned i, unsigned lane) {
+__device__ __forceinline__ int fb_walk_ray(const FbRayArgs &a, unsigned i, unsigned lane, int start) {
   uint32_t *claims = a.stamp[0];
   const unsigned fr = a.frame_tag << FB_CLAIM_FRAME_SHIFT;
   const int L = a.ray_len[i];
   const uint32_t *row = a.ray_list + (long long)i * a.cap;
   int result = L;
-  for (int t0 = 0; t0 < L; t0 += 32) {
+  // Everything before `start` is still claimed by this ray (a displacement there would have lowered `start`), so the walk
+  // resumes at the 32-aligned chunk holding it.  Two-deep software pipeline: the list entries of chunk c+2 and the claim
+  // words of chunk c+1 are in flight while chunk c is resolved (a stale claim word is caught by the CAS / the next check).
+  int t0 = start & ~31;
+  unsigned e = (FB_CLS_SKIP << 30), e1 = (FB_CLS_SKIP << 30), seen = 0;
+  if (t0 + (int)lane < L) e = __ldcg(&row[L - 1 - (t0 + (int)lane)]);
+  if (t0 + 32 + (int)lane < L) e1 = __ldcg(&row[L - 1 - (t0 + 32 + (int)lane)]);
+  if ((e >> 30) == FB_CLS_COUNT || (e >> 30) == FB_CLS_STAMP) seen = __ldcg(&claims[e & FB_LIST_IDX_MASK]);
+  for (; t0 < L; t0 += 32) {
     const int t = t0 + (int)lane;
-    unsigned e = (FB_CLS_SKIP << 30);
-    if (t < L) e = __ldcg(&row[L - 1 - t]);
+    unsigned e2 = (FB_CLS_SKIP << 30), seen1 = 0;
+    if (t + 64 < L) e2 = __ldcg(&row[L - 1 - (t + 64)]);
+    if ((e1 >> 30) == FB_CLS_COUNT || (e1 >> 30) == FB_CLS_STAMP) seen1 = __ldcg(&claims[e1 & FB_LIST_IDX_MASK]);
     const unsigned cls = e >> 30, ii = e & FB_LIST_IDX_MASK;
     const bool normal = cls == FB_CLS_COUNT || cls == FB_CLS_STAMP;
     const unsigned mine = fr | (i << FB_POS_BITS) | (unsigned)t;
     int st = 0;                           // 0 = passable & already mine, 1 = passable & must be claimed, 2 = blocked
-    unsigned seen = 0;
-    if (normal) {
-      seen = __ldcg(&claims[ii]);
-      if (seen != mine) st = fb_claim_blocks(a, seen, i) ? 2 : 1;
-    }
+    if (normal && seen != mine) st = fb_claim_blocks(a, seen, i) ? 2 : 1;
     const unsigned m = __ballot_sync(0xffffffffu, st == 2 || cls == FB_CLS_STOP);
     const int first = m ? (__ffs(m) - 1) : 32;
     while (st == 1 && (int)lane < first) {                    // claim; a failed CAS means someone else wrote: look again
       const unsigned old = atomicCAS(&claims[ii], seen, mine);
       if (old == seen) {
         st = 0;
-        if ((old >> FB_CLAIM_FRAME_SHIFT) == a.frame_tag) {   // displaced a (higher) ray: it has to walk again
+        if ((old >> FB_CLAIM_FRAME_SHIFT) == a.frame_tag) {   // displaced a (higher) ray: it has to walk again from there
           const unsigned k = (old >> FB_POS_BITS) & FB_RAY_MASK;
-          if (k != i) { __threadfence(); a.ray_dirty[k] = 1u; }
+          if (k != i) { __threadfence(); atomicMin(&a.ray_dirty[k], old & FB_POS_MASK); }
         }
         break;
       }
@@ -273,6 +279,7 @@ __device__ __forceinline__ int fb_walk_ray(const FbRayArgs &a, unsigned i, unsig
       result = (t0 + f2) | (by_stamp ? FB_REACH_BLOCKED : 0);
       break;
     }
+    e = e1; e1 = e2; seen = seen1;
   }
   return result;
 }
@@ -293,38 +300,64 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_ray_resolve(FbGeom g, FbRayAr
   unsigned round = 0;
   for (;;) {
     ++round;
+    unsigned long long t_a = 0, t_b = 0;
+    if (a.dbg && gt == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
     unsigned *work_n = &a.ctr->ray_work[round % 3u];
     for (long long i = gt; i < a.n; i += nthreads) {
       const int L = a.ray_len[i];
       bool need = false;
+      int start = 0;
       if (L > 0) {
-        if (round == 1u || a.ray_dirty[i]) need = true;
+        if (round == 1u) { need = true; a.ray_dirty[i] = FB_RAY_CLEAN; }
         else {
-          const int rr = a.ray_reach[i];
-          if (rr & FB_REACH_BLOCKED) {
-            const unsigned e = __ldcg(&a.ray_list[i * a.cap + (L - 1 - (rr & ~FB_REACH_BLOCKED))]);
+          const unsigned dp = a.ray_dirty[i];                 // lowest position a lower ray displaced this one from
+          if (dp != FB_RAY_CLEAN) a.ray_dirty[i] = FB_RAY_CLEAN;
+          const int rr = a.ray_reach[i], rpos = rr & ~FB_REACH_BLOCKED;
+          if (dp < (unsigned)rpos) { need = true; start = (int)dp; }   // (a displaced claim beyond the reach was stale anyway)
+          else if (rr & FB_REACH_BLOCKED) {
+            const unsigned e = __ldcg(&a.ray_list[i * a.cap + (L - 1 - rpos)]);
             need = !fb_claim_blocks(a, __ldcg(&claims[e & FB_LIST_IDX_MASK]), (unsigned)i);
+            start = rpos;
           }
         }
       }
       const unsigned slot = fb_warp_append(work_n, need);
-      if (need) { a.ray_act[slot] = (unsigned)i; a.ray_dirty[i] = 0u; }
+      if (need) { a.ray_act[slot] = (unsigned)i; a.ray_act[a.n + slot] = (unsigned)start; }
     }
     grid.sync();
     const unsigned nw = __ldcg(work_n);
     if (blockIdx.x == 0 && threadIdx.x == 0) a.ctr->ray_work[(round + 2u) % 3u] = 0u;   // next used two barriers from now
     if (nw == 0u || round >= a.max_rounds) break;
-    for (unsigned p = gw; p < nw; p += nwarps) {
-      const unsigned i = __ldcg(&a.ray_act[p]);
-      const int result = fb_walk_ray(a, i, lane);
-      if (lane == 0) a.ray_reach[i] = result;
+    if (a.dbg && gt == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_b));
+    if (round == 1u) {
+      // Contiguous index blocks per warp: neighbouring rays (which share most voxels) are resolved in serial order by one
+      // warp, so far fewer optimistic claims have to be taken back in the later rounds.
+      const long long per = (a.n + nwarps - 1) / nwarps;
+      const long long hi = min((long long)(gw + 1) * per, a.n);
+      for (long long i = (long long)gw * per; i < hi; ++i) {
+        if (a.ray_len[i] <= 0) continue;
+        const int result = fb_walk_ray(a, (unsigned)i, lane, 0);
+        if (lane == 0) a.ray_reach[i] = result;
+      }
+    } else {
+      for (unsigned p = gw; p < nw; p += nwarps) {
+        const unsigned i = __ldcg(&a.ray_act[p]);
+        const int result = fb_walk_ray(a, i, lane, (int)__ldcg(&a.ray_act[a.n + p]));
+        if (lane == 0) a.ray_reach[i] = result;
+      }
     }
     grid.sync();
+    if (a.dbg && gt == 0 && round < 300u) {
+      unsigned long long t_c; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_c));
+      a.dbg[3 * round] = nw; a.dbg[3 * round + 1] = t_b - t_a; a.dbg[3 * round + 2] = t_c - t_b;
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.ctr->ray_rounds = round;
     if (round >= a.max_rounds) a.ctr->ray_error = 3u;
   }
+  unsigned long long t_d = 0;
+  if (a.dbg && gt == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_d));
   // ---- counts: SetOccupancy(tmp, 0) for every visited voxel, including the one that stopped the walk (Fiesta.h:248-268)
   for (long long i = gw; i < a.n; i += nwarps) {
     const int L = a.ray_len[i];
@@ -332,12 +365,18 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_ray_resolve(FbGeom g, FbRayAr
     const int rr = a.ray_reach[i];
     const int R = (rr & ~FB_REACH_BLOCKED) + ((rr & FB_REACH_BLOCKED) ? 1 : 0);
     const uint32_t *row = a.ray_list + (long long)i * a.cap;
-    for (int t0 = 0; t0 < R; t0 += 32) {
-      const int t = t0 + (int)lane;
-      bool cnt = false; unsigned ii = 0;
-      if (t < R) { const unsigned e = __ldcg(&row[L - 1 - t]); cnt = (e >> 30) == FB_CLS_COUNT; ii = e & FB_LIST_IDX_MASK; }
-      if (cnt) fb_count(g, a, ii, 0u, (unsigned long long)i, 1u + (unsigned)t);
+    for (int t0 = 0; t0 < R; t0 += 128) {                     // four independent list loads in flight per lane
+      unsigned e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int t = t0 + 32 * u + (int)lane; e[u] = t < R ? __ldcg(&row[L - 1 - t]) : (FB_CLS_SKIP << 30); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if ((e[u] >> 30) == FB_CLS_COUNT) fb_count(g, a, e[u] & FB_LIST_IDX_MASK, 0u, (unsigned long long)i, 1u + (unsigned)(t0 + 32 * u + (int)lane));
     }
+  }
+  if (a.dbg) {
+    grid.sync();
+    if (gt == 0) { unsigned long long t_e; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_e)); a.dbg[0] = t_e - t_d; }
   }
 }
 
