@@ -118,18 +118,23 @@ __device__ __forceinline__ void tma_load_box(void *dst, const CUtensorMap *tmap,
       : "memory");
 }
 
-#define WF_THREADS 256     // 2 voxels per thread (x and x+4): four CTAs = four independent tile pipelines per SM
+#define WF_THREADS 256     // a thread owns 2 voxels (x and x+4) of the tile; four CTAs = four independent tile pipelines per SM
 
 __global__ void __launch_bounds__(WF_THREADS, 4)
 k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
-  // buf[0], buf[1]: TMA landing buffers (tile k in buf[k&1], tile k+1 prefetched into the other); buf[2]: relaxation partner
-  __shared__ __align__(128) uint32_t buf[3][FB_BOX_WORDS];
+  // buf[0], buf[1]: TMA landing buffers (tile k in buf[k&1], tile k+1 prefetched into the other); a tile is relaxed in place
+  __shared__ __align__(128) uint32_t buf[2][FB_BOX_WORDS];
   __shared__ __align__(8) uint64_t mbar[2];
   __shared__ int s_bbox[6];
   __shared__ unsigned s_next[3];            // {work index, tile id, 1 = needs a full visit} of the prefetched item
-  // per z-row bit masks of the FRESH flags (bit = box z index), one set per relaxation buffer: lets a voxel find out with
-  // 13 loads whether anything within reach is in the queue before it pays for the 24-neighbour evaluation
-  __shared__ uint32_t fmask[2][FB_BOX * FB_BOX];
+  // per z-row bit masks of the FRESH flags (bit = box z index): a voxel finds out with 13 loads which of its 24 neighbours
+  // are in the queue.  fm_halo keeps the (constant) halo bits, fm additionally the interior voxels changed last iteration.
+  __shared__ uint32_t fm[FB_BOX * FB_BOX], fm_halo[FB_BOX * FB_BOX];
+  // active list of one local iteration: voxel (lx<<6|ly<<3|lz), candidate mask (bit k = direction kd[k]), result
+  __shared__ unsigned short listV[FB_TILE * FB_TILE * FB_TILE];
+  __shared__ uint32_t listF[FB_TILE * FB_TILE * FB_TILE], res[FB_TILE * FB_TILE * FB_TILE];
+  __shared__ unsigned s_cnt[2];
+  __shared__ int s_koff[24];
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   const int ly = (tid >> 3) & 7, lz = tid & 7;
@@ -139,11 +144,16 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
     lxh[h] = (tid >> 6) + 4 * h;
     sh[h] = (lxh[h] + FB_HALO) * (FB_BOX * FB_BOXZ) + (ly + FB_HALO) * FB_BOXZ + (lz + FB_ZPAD);
   }
-  // parameters.h:55-68 again, as compile-time immediates for the unrolled relaxation loop
-  constexpr int kd[24][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
-                             {-1, -1, 0}, {1, 1, 0}, {0, -1, -1}, {0, 1, 1}, {-1, 0, -1}, {1, 0, 1},
-                             {-1, 1, 0}, {1, -1, 0}, {0, -1, 1}, {0, 1, -1}, {1, 0, -1}, {-1, 0, 1},
-                             {-2, 0, 0}, {2, 0, 0}, {0, -2, 0}, {0, 2, 0}, {0, 0, -2}, {0, 0, 2}};
+  // dirs_ (parameters.h:55-68) grouped by z-row so that the queue bits of all 24 neighbours come out of 13 mask words:
+  // same row dz = -2,-1,+1,+2 | rows x-1, x+1, y-1, y+1 with dz = -1,0,+1 | the four xy diagonals | x-2, x+2, y-2, y+2
+  constexpr int kd[24][3] = {{0, 0, -2}, {0, 0, -1}, {0, 0, 1}, {0, 0, 2},
+                             {-1, 0, -1}, {-1, 0, 0}, {-1, 0, 1}, {1, 0, -1}, {1, 0, 0}, {1, 0, 1},
+                             {0, -1, -1}, {0, -1, 0}, {0, -1, 1}, {0, 1, -1}, {0, 1, 0}, {0, 1, 1},
+                             {-1, -1, 0}, {-1, 1, 0}, {1, -1, 0}, {1, 1, 0},
+                             {-2, 0, 0}, {2, 0, 0}, {0, -2, 0}, {0, 2, 0}};
+#pragma unroll
+  for (int k = 0; k < 24; ++k)
+    if (tid == k) s_koff[k] = kd[k][0] * (FB_BOX * FB_BOXZ) + kd[k][1] * FB_BOXZ + kd[k][2];
 
   if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
   __syncthreads();
@@ -215,25 +225,31 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
       }
       mbar_wait(&mbar[slot], parity[slot]);
       parity[slot] ^= 1u;
-      uint32_t *L = buf[slot], *S = buf[2];
-      for (int k = tid; k < FB_BOX_WORDS; k += WF_THREADS) S[k] = L[k];   // the halo must exist in both relaxation buffers
-      if (tid < FB_BOX * FB_BOX) {                            // FRESH mask of every z-row of the box (halo bits never change)
+      uint32_t *V = buf[slot];
+      if (tid < FB_BOX * FB_BOX) {                            // FRESH mask of every z-row of the box
         uint32_t mk = 0;
 #pragma unroll
-        for (int z = 0; z < FB_BOXZ; ++z) mk |= (L[tid * FB_BOXZ + z] >> 31) << z;
-        fmask[0][tid] = mk; fmask[1][tid] = mk;
+        for (int z = 0; z < FB_BOXZ; ++z) mk |= (V[tid * FB_BOXZ + z] >> 31) << z;
+        const int rx = tid / FB_BOX, ry = tid % FB_BOX;
+        const bool inner = rx >= FB_HALO && rx < FB_HALO + FB_TILE && ry >= FB_HALO && ry < FB_HALO + FB_TILE;
+        fm[tid] = mk;
+        fm_halo[tid] = inner ? (mk & ~(0xffu << FB_ZPAD)) : mk;
       }
-      uint32_t orig[2], mine[2], fresh[2], nmask[2];
-      bool updatable[2];
+      if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+      uint32_t orig[2], mine[2], nmask[2];
+      bool updatable[2], pulls[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int vx = x0 + lxh[h];
-        orig[h] = L[sh[h]];
-        mine[h] = orig[h] & FB_CODE_MASK;                     // code without the flag
-        fresh[h] = orig[h] >> 31;                             // changed in the previous generation (global flag)
+        orig[h] = V[sh[h]];
         // A voxel relaxes iff it has been observed (unknown voxels are barriers: distance_ = -10000 is never > tmp,
         // ESDFMap.cpp:382) and lies inside the update box (only in-box voxels are ever queued, ESDFMap.cpp:351,378).
-        updatable[h] = mine[h] != FB_UNKNOWN && fb_in_range(g, vx, vy, vz);
+        updatable[h] = (orig[h] & FB_CODE_MASK) != FB_UNKNOWN && fb_in_range(g, vx, vy, vz);
+        // With the whole grid in the update box every value a neighbour holds was offered to this voxel when it was set
+        // (the neighbour was in the queue then) and records only improve -- so the pull of a queued voxel (ESDFMap.cpp:
+        // 349-367) can only find something new if its own record was (re)set to "no obstacle": first observation or a
+        // deleted obstacle.  With a moving update box (VoxInRange, :351) that does not hold and every queued voxel pulls.
+        pulls[h] = !g.box_is_full || (orig[h] & FB_CODE_MASK) == FB_INF;
         nmask[h] = 0xffffffu;
         if (!g.box_is_full) {                                 // VoxInRange(new_pos), ESDFMap.cpp:351
           nmask[h] = 0;
@@ -243,57 +259,104 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
         }
       }
       __syncthreads();
-      int cb = 0;                                             // 0: read L / write S, 1: read S / write L
-      for (;;) {
-        const uint32_t *b = cb ? S : L;
-        uint32_t *o = cb ? L : S;
-        const uint32_t *fm = fmask[cb];
-        unsigned anyfresh = 0;
+      // Local Jacobi iterations.  (A) every thread derives, for its two voxels, the set of neighbours whose value it has to
+      // look at -- the ones in the queue (their push, ESDFMap.cpp:375-391) or all of them when the voxel itself pulls --
+      // and lists the voxel if that set is not empty; (B) the listed voxels are evaluated by groups of four lanes (six
+      // directions each, only the set bits), which turns the sparse, clustered activity of a wave front into dense work for
+      // all warps; (C) the improvements are applied and become the queue of the next iteration.
+      for (int it = 0;; ++it) {
+        const int par2 = it & 1;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          uint32_t best = mine[h];
-          bool active = false;
+          uint32_t F = 0;
           if (updatable[h]) {
             const int r = (lxh[h] + FB_HALO) * FB_BOX + (ly + FB_HALO), zb = lz + FB_ZPAD;
-            const uint32_t any5 = (fm[r] >> (zb - 2)) & 0x1fu;                                   // self, z+-1, z+-2
-            const uint32_t any3 = ((fm[r - FB_BOX] | fm[r + FB_BOX] | fm[r - 1] | fm[r + 1]) >> (zb - 1)) & 7u;   // x+-1 / y+-1 rows
-            const uint32_t any1 = ((fm[r - FB_BOX - 1] | fm[r - FB_BOX + 1] | fm[r + FB_BOX - 1] | fm[r + FB_BOX + 1] |
-                                    fm[r - 2 * FB_BOX] | fm[r + 2 * FB_BOX] | fm[r - 2] | fm[r + 2]) >> zb) & 1u;   // diagonals, +-2 steps
-            active = (any5 | any3 | any1) != 0u;
+            const uint32_t m0 = fm[r];
+            F = ((m0 >> (zb - 2)) & 3u) | (((m0 >> (zb + 1)) & 3u) << 2) |
+                (((fm[r - FB_BOX] >> (zb - 1)) & 7u) << 4) | (((fm[r + FB_BOX] >> (zb - 1)) & 7u) << 7) |
+                (((fm[r - 1] >> (zb - 1)) & 7u) << 10) | (((fm[r + 1] >> (zb - 1)) & 7u) << 13) |
+                (((fm[r - FB_BOX - 1] >> zb) & 1u) << 16) | (((fm[r - FB_BOX + 1] >> zb) & 1u) << 17) |
+                (((fm[r + FB_BOX - 1] >> zb) & 1u) << 18) | (((fm[r + FB_BOX + 1] >> zb) & 1u) << 19) |
+                (((fm[r - 2 * FB_BOX] >> zb) & 1u) << 20) | (((fm[r + 2 * FB_BOX] >> zb) & 1u) << 21) |
+                (((fm[r - 2] >> zb) & 1u) << 22) | (((fm[r + 2] >> zb) & 1u) << 23);
+            if (pulls[h] && ((m0 >> zb) & 1u)) F = 0xffffffu;
+            F &= nmask[h];
           }
-          if (active) {
-            const int vx = x0 + lxh[h];
+          const uint32_t bal = __ballot_sync(0xffffffffu, F != 0u);
+          if (bal) {
+            const int lane = tid & 31;
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&s_cnt[par2], (unsigned)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (F) {
+              const unsigned pos = base + (unsigned)__popc(bal & ((1u << lane) - 1u));
+              listV[pos] = (unsigned short)((lxh[h] << 6) | (ly << 3) | lz);
+              listF[pos] = F;
+            }
+          }
+        }
+        __syncthreads();
+        const int n = (int)s_cnt[par2];
+        if (n == 0) break;
+        if (tid < FB_BOX * FB_BOX) fm[tid] = fm_halo[tid];
+        if (tid == 0) s_cnt[par2 ^ 1] = 0;
+        int anych = 0;
+        {
+          const int lane = tid & 31, sub = lane & 3;
+          for (int e0 = (tid >> 5) * 8; e0 < n; e0 += (WF_THREADS / 32) * 8) {
+            const int e = e0 + (lane >> 2);
+            const bool valid = e < n;
+            uint32_t self = 0, best = 0, m = 0;
             unsigned bestd = 0xffffffffu;
-            if (best >= 2u) { int ox, oy, oz; fb_unpack(best, ox, oy, oz); ox -= vx; oy -= vy; oz -= vz; bestd = (unsigned)(ox * ox + oy * oy + oz * oz); }
-#pragma unroll
-            for (int k = 0; k < 24; ++k) {
-              const uint32_t wn = b[sh[h] + kd[k][0] * (FB_BOX * FB_BOXZ) + kd[k][1] * FB_BOXZ + kd[k][2]];
-              const uint32_t c = wn & FB_CODE_MASK;
-              // candidate iff the neighbour has a closest obstacle (ESDFMap.cpp:353) and either it is in the queue (its
-              // push phase, :375-391) or this voxel is (its pull phase, :349-367)
-              if (c >= 2u && c != best && ((nmask[h] >> k) & 1u) && ((wn >> 31) | fresh[h])) {   // c == best cannot improve (same obstacle)
-                int ox, oy, oz; fb_unpack(c, ox, oy, oz); ox -= vx; oy -= vy; oz -= vz;
+            int sidx = 0, vx = 0, wy = 0, wz = 0;
+            if (valid) {
+              const int v = listV[e];
+              const int lx = v >> 6, ly2 = (v >> 3) & 7, lz2 = v & 7;
+              sidx = (lx + FB_HALO) * (FB_BOX * FB_BOXZ) + (ly2 + FB_HALO) * FB_BOXZ + (lz2 + FB_ZPAD);
+              vx = x0 + lx; wy = y0 + ly2; wz = z0 + lz2;
+              self = V[sidx] & FB_CODE_MASK;
+              best = self;
+              if (best >= 2u) { int ox, oy, oz; fb_unpack(best, ox, oy, oz); ox -= vx; oy -= wy; oz -= wz; bestd = (unsigned)(ox * ox + oy * oy + oz * oz); }
+              m = listF[e] & (0x111111u << sub);
+            }
+            while (m) {
+              const int k = __ffs(m) - 1;
+              m &= m - 1u;
+              const uint32_t c = V[sidx + s_koff[k]] & FB_CODE_MASK;
+              if (c >= 2u && c != best) {                     // the neighbour has a closest obstacle (ESDFMap.cpp:353)
+                int ox, oy, oz; fb_unpack(c, ox, oy, oz); ox -= vx; oy -= wy; oz -= wz;
                 const unsigned d = (unsigned)(ox * ox + oy * oy + oz * oz);
                 if (d < bestd || (d == bestd && c < best)) { bestd = d; best = c; }   // strict improvement; ties -> smallest coordinate
               }
             }
+#pragma unroll
+            for (int off = 1; off <= 2; off <<= 1) {
+              const unsigned od = __shfl_xor_sync(0xffffffffu, bestd, off);
+              const uint32_t oc = __shfl_xor_sync(0xffffffffu, best, off);
+              if (od < bestd || (od == bestd && oc < best)) { bestd = od; best = oc; }
+            }
+            if (valid && sub == 0) {
+              const bool ch = best != self;
+              res[e] = ch ? best : 0u;
+              anych |= ch ? 1 : 0;
+            }
           }
-          fresh[h] = best != mine[h] ? 1u : 0u;
-          mine[h] = best;
-          o[sh[h]] = best | (fresh[h] << 31);
-          // a warp owns 4 interior z-rows per h: lanes 8r..8r+7 = row (lx, ly0 + r)
-          const uint32_t bal = __ballot_sync(0xffffffffu, fresh[h] != 0u);
-          const int lane = tid & 31;
-          if (lane < 4) {
-            const int r = (lxh[h] + FB_HALO) * FB_BOX + (((tid >> 5) & 1) * 4 + lane + FB_HALO);
-            fmask[cb ^ 1][r] = (fm[r] & ~(0xffu << FB_ZPAD)) | (((bal >> (8 * lane)) & 0xffu) << FB_ZPAD);
-          }
-          anyfresh |= fresh[h];
         }
-        const int any = __syncthreads_or((int)anyfresh);
-        cb ^= 1;
+        const int any = __syncthreads_or(anych);
         if (!any) break;
+        for (int e = tid; e < n; e += WF_THREADS) {
+          const uint32_t rr = res[e];
+          if (rr) {
+            const int v = listV[e];
+            const int lx = v >> 6, ly2 = (v >> 3) & 7, lz2 = v & 7;
+            V[(lx + FB_HALO) * (FB_BOX * FB_BOXZ) + (ly2 + FB_HALO) * FB_BOXZ + (lz2 + FB_ZPAD)] = rr;
+            atomicOr(&fm[(lx + FB_HALO) * FB_BOX + (ly2 + FB_HALO)], 1u << (lz2 + FB_ZPAD));
+          }
+        }
+        __syncthreads();
       }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) mine[h] = V[sh[h]] & FB_CODE_MASK;
       int nch = 0;
       bool diff = false;
       uint32_t outw[2];

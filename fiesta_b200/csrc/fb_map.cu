@@ -558,7 +558,7 @@ int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, co
   a.ray_list = m->ray_list; a.ray_len = m->ray_len; a.ray_reach = m->ray_reach; a.ray_act = m->ray_act; a.ray_dirty = m->ray_dirty; a.ctr = m->d_ctr;
   static const bool dbg_ray = getenv("FIESTA_DEBUG_RAY") != nullptr;
   a.dbg = nullptr;
-  if (dbg_ray) { if (!m->d_dbg) CK(cudaMalloc((void **)&m->d_dbg, 1024 * 8)); CK(cudaMemsetAsync(m->d_dbg, 0, 1024 * 8, m->stream)); a.dbg = m->d_dbg; }
+  if (dbg_ray) { if (!m->d_dbg) CK(cudaMalloc((void **)&m->d_dbg, 2048 * 8)); CK(cudaMemsetAsync(m->d_dbg, 0, 2048 * 8, m->stream)); a.dbg = m->d_dbg; }
   CK(cudaEventRecord(m->ev[0], m->stream));
   k_reset_ray_ctr<<<1, 1, 0, m->stream>>>(m->d_ctr);
   int launches = 1;
@@ -714,7 +714,7 @@ int fiesta_update_esdf(fiesta_map *m) {
   a.tile_x_lo = m->tile_x_lo; a.tile_x_hi = m->tile_x_hi;
   a.dbg = nullptr;
   static const bool dbg_wf = getenv("FIESTA_DEBUG_WF") != nullptr;
-  if (dbg_wf) { if (!m->d_dbg) CK(cudaMalloc((void **)&m->d_dbg, 1024 * 8)); CK(cudaMemsetAsync(m->d_dbg, 0, 1024 * 8, m->stream)); a.dbg = m->d_dbg; }
+  if (dbg_wf) { if (!m->d_dbg) CK(cudaMalloc((void **)&m->d_dbg, 2048 * 8)); CK(cudaMemsetAsync(m->d_dbg, 0, 2048 * 8, m->stream)); a.dbg = m->d_dbg; }
   CK(cudaEventRecord(m->ev[0], m->stream));
   k_reset_esdf_ctr<<<1, 1, 0, m->stream>>>(m->d_ctr);
   m->st.kernel_launches++;
@@ -735,8 +735,14 @@ int fiesta_update_esdf(fiesta_map *m) {
   m->st.voxels_changed = (int64_t)m->h_ctr->voxels_changed; m->st.voxels_reset = (int64_t)m->h_ctr->voxels_reset;
   m->st.tile_visits = (int64_t)m->h_ctr->tile_visits; m->st.generations = m->h_ctr->generations;
   if (a.dbg) {
-    unsigned long long h[1024];
+    unsigned long long h[2048];
     CK(cudaMemcpy(h, m->d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h[1024 + 4] || h[1024 + 5]) {                      // only filled by a build with FB_WF_PROFILE
+      const unsigned long long *q = h + 1024;
+      const double nf = q[4] ? (double)q[4] : 1.0, nr = q[5] ? (double)q[5] : 1.0;
+      fprintf(stderr, "[wfprof] full %llu (cycles/visit: pre %.0f iterate %.0f epilogue %.0f; iterations %.2f entries/iter %.1f) retire-only %llu (%.0f cycles)\n",
+              q[4], q[0] / nf, q[1] / nf, q[2] / nf, q[6] / nf, q[6] ? (double)q[7] / (double)q[6] : 0.0, q[5], q[3] / nr);
+    }
     fprintf(stderr, "[wf] gens=%u", m->h_ctr->generations);
     for (unsigned gI = 0; gI < m->h_ctr->generations && gI < 256; ++gI) fprintf(stderr, " | %llu/%llu %.0f+%.0fus", h[4 * gI], h[4 * gI + 1], h[4 * gI + 2] * 1e-3, h[4 * gI + 3] * 1e-3);
     fprintf(stderr, "\n");
