@@ -179,8 +179,7 @@ struct FbRayArgs {
   unsigned long long key_base;
   uint32_t *ray_list;     // [n][cap] row-major, reversed (t = 0 is the voxel before the last emitted one)
   int *ray_len, *ray_reach;
-  unsigned *ray_act;      // per-round work list: rays that have to walk again
-  unsigned *ray_dirty;    // ray was displaced from a voxel by a lower ray since its last walk
+  unsigned *ray_dirty;    // lowest list position a lower ray displaced this ray from since its last walk (FB_RAY_CLEAN: none)
   int cap;
   unsigned frame_tag;     // claim frame tag (1..3)
   unsigned owner_tag;     // endpoint-owner frame tag

@@ -53,7 +53,7 @@ struct fiesta_map {
   // ray casting
   float *d_xyz; size_t cap_xyz;
   uint32_t *ray_list; size_t cap_ray_list;
-  int *ray_len, *ray_reach; unsigned *ray_act, *ray_dirty; size_t cap_rays;
+  int *ray_len, *ray_reach; unsigned *ray_dirty; size_t cap_rays;
   unsigned frame_tag, owner_tag;
   // queries
   double *d_qin, *d_qout; size_t cap_q;
@@ -318,7 +318,7 @@ void fiesta_destroy(fiesta_map *m) {
   if (m->stream) cudaStreamSynchronize(m->stream);
   void *dev[] = {m->cobs, m->cobs_b, m->stamp[0], m->stamp[1], m->occbits, m->occ, m->cnt, m->tile_flag, m->nb_flag, m->list[0], m->list[1],
                  m->changed[0], m->changed[1], m->changed_bbox[0], m->changed_bbox[1], m->touch_flag, m->touch_list, m->ins, m->del, m->d_ctr, m->d_ev,
-                 m->d_xyz, m->ray_list, m->ray_len, m->ray_reach, m->ray_act, m->ray_dirty, m->d_qin, m->d_qout};
+                 m->d_xyz, m->ray_list, m->ray_len, m->ray_reach, m->ray_dirty, m->d_qin, m->d_qout};
   for (void *p : dev) if (p) cudaFree(p);
   if (m->mode == FIESTA_MODE_EXACT) fb_exact_free(&m->X);
   if (m->d_dbg) cudaFree(m->d_dbg);
@@ -540,14 +540,12 @@ int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, co
   int r;
   size_t need_rays = (size_t)n;
   if (need_rays > m->cap_rays) {
-    size_t c1 = m->cap_rays, c2 = m->cap_rays, c3 = m->cap_rays, c4 = m->cap_rays;
+    size_t c1 = m->cap_rays, c2 = m->cap_rays, c4 = m->cap_rays;
     if ((r = ensure(&m->ray_len, &c1, need_rays, false, m->stream))) return r;
     if ((r = ensure(&m->ray_reach, &c2, need_rays, false, m->stream))) return r;
-    if ((r = ensure(&m->ray_act, &c3, 2 * need_rays, false, m->stream))) return r;
     if ((r = ensure(&m->ray_dirty, &c4, need_rays, false, m->stream))) return r;
     m->cap_rays = c1;
     if (c2 < m->cap_rays) m->cap_rays = c2;
-    if (c3 / 2 < m->cap_rays) m->cap_rays = c3 / 2;
     if (c4 < m->cap_rays) m->cap_rays = c4;
   }
   if ((r = ensure(&m->ray_list, &m->cap_ray_list, (size_t)a.cap * (size_t)n, false, m->stream))) return r;
@@ -555,7 +553,7 @@ int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, co
   a.touch_flag = m->touch_flag; a.touch_list = m->touch_list; a.touch_epoch = m->touch_epoch;
   a.tkey = m->mode == FIESTA_MODE_EXACT ? m->X.tkey : nullptr; a.xtouched = m->X.touched; a.key_base = m->X.key_base;
   m->X.key_base += 1ull << 30;
-  a.ray_list = m->ray_list; a.ray_len = m->ray_len; a.ray_reach = m->ray_reach; a.ray_act = m->ray_act; a.ray_dirty = m->ray_dirty; a.ctr = m->d_ctr;
+  a.ray_list = m->ray_list; a.ray_len = m->ray_len; a.ray_reach = m->ray_reach; a.ray_dirty = m->ray_dirty; a.ctr = m->d_ctr;
   static const bool dbg_ray = getenv("FIESTA_DEBUG_RAY") != nullptr;
   a.dbg = nullptr;
   if (dbg_ray) { if (!m->d_dbg) CK(cudaMalloc((void **)&m->d_dbg, 2048 * 8)); CK(cudaMemsetAsync(m->d_dbg, 0, 2048 * 8, m->stream)); a.dbg = m->d_dbg; }
@@ -574,7 +572,7 @@ int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, co
     unsigned long long h[1024];
     CK(cudaMemcpy(h, m->d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
     fprintf(stderr, "[ray] rounds=%u counts %.0fus", m->h_ctr->ray_rounds, h[0] * 1e-3);
-    for (unsigned r2 = 1; r2 < m->h_ctr->ray_rounds && r2 < 300; ++r2) fprintf(stderr, " | %llu %.0f+%.0fus", h[3 * r2], h[3 * r2 + 1] * 1e-3, h[3 * r2 + 2] * 1e-3);
+    for (unsigned r2 = 1; r2 <= m->h_ctr->ray_rounds && r2 < 300; ++r2) fprintf(stderr, " | %llu %.0fus", h[3 * r2], h[3 * r2 + 2] * 1e-3);
     fprintf(stderr, "\n");
   }
   if (m->h_ctr->ray_error == 3) { set_error("fiesta_raycast_frame: stamp resolution did not converge"); return FIESTA_ERR_LIMIT; }

@@ -108,6 +108,8 @@ __global__ void k_ray_endpoints(FbGeom g, FbRayArgs a) {
   a.ray_len[i] = len;
 }
 
+#define FB_RAY_CLEAN 0xffffffffu   // ray_dirty: no lower ray has displaced this one since its last walk
+
 // ---------------------------------------------------------------- DDA
 struct FbDda {
   int c[3], e[3], step[3];
@@ -214,6 +216,7 @@ __global__ void k_ray_trace(FbGeom g, FbRayArgs a) {
   if (L > a.cap) { L = 0; atomicExch(&a.ctr->ray_error, 2u); atomicAdd(&a.ctr->rays_dropped, 1u); }
   a.ray_len[i] = L;
   a.ray_reach[i] = L;                                         // optimistic: claims made while walking count as valid
+  a.ray_dirty[i] = FB_RAY_CLEAN;
   if (L) atomicAdd(&a.ctr->ray_voxels, (unsigned long long)L);
 }
 
@@ -221,7 +224,6 @@ __global__ void k_ray_trace(FbGeom g, FbRayArgs a) {
 // One warp per ray.  reach[i] = index at which the back-walk stops (L if it runs off the list) | FB_REACH_BLOCKED when it
 // stopped at a voxel stamped by an earlier ray (that voxel is still counted, Fiesta.h:248-268).
 #define FB_REACH_BLOCKED 0x40000000
-#define FB_RAY_CLEAN 0xffffffffu
 
 // Is the voxel whose claim word is `seen` validly claimed by a ray with a lower index than `i`?
 __device__ __forceinline__ bool fb_claim_blocks(const FbRayArgs &a, unsigned seen, unsigned i) {
@@ -293,64 +295,72 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_ray_resolve(FbGeom g, FbRayAr
   const unsigned gt = blockIdx.x * RR_THREADS + threadIdx.x, nthreads = gridDim.x * RR_THREADS;
   const uint32_t *claims = a.stamp[0];
 
-  // Event-driven rounds.  Each round: (check) one thread per cast ray decides whether the ray has to walk again: it was
-  // displaced by a lower ray (dirty), or the claim that stopped it is no longer valid; (walk) one warp per listed ray.
-  // A ray whose claims are intact and whose blocker is still valid would walk to exactly the same result, so skipping it
-  // is exact.  Round 1 walks everything.  The loop ends when a check finds nothing to do.
+  // Event-driven rounds, one grid barrier each.  Round 1 walks every ray.  In a later round each lane looks at one ray and
+  // decides whether it has to walk again: a lower ray displaced it from a voxel (dirty position), or the claim that stopped
+  // it is no longer valid; the warp then walks those rays from the position in question.  A ray whose claims are intact
+  // and whose blocker is still valid would walk to exactly the same result, so skipping it is exact.  Checks run
+  // concurrently with the walks of other warps and may see stale state -- but only walks change state, so the first round
+  // without any walk has seen the final state everywhere, and that is where the loop ends.
   unsigned round = 0;
   for (;;) {
     ++round;
-    unsigned long long t_a = 0, t_b = 0;
+    unsigned long long t_a = 0;
     if (a.dbg && gt == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
     unsigned *work_n = &a.ctr->ray_work[round % 3u];
-    for (long long i = gt; i < a.n; i += nthreads) {
-      const int L = a.ray_len[i];
-      bool need = false;
-      int start = 0;
-      if (L > 0) {
-        if (round == 1u) { need = true; a.ray_dirty[i] = FB_RAY_CLEAN; }
-        else {
-          const unsigned dp = a.ray_dirty[i];                 // lowest position a lower ray displaced this one from
-          if (dp != FB_RAY_CLEAN) a.ray_dirty[i] = FB_RAY_CLEAN;
-          const int rr = a.ray_reach[i], rpos = rr & ~FB_REACH_BLOCKED;
-          if (dp < (unsigned)rpos) { need = true; start = (int)dp; }   // (a displaced claim beyond the reach was stale anyway)
-          else if (rr & FB_REACH_BLOCKED) {
-            const unsigned e = __ldcg(&a.ray_list[i * a.cap + (L - 1 - rpos)]);
-            need = !fb_claim_blocks(a, __ldcg(&claims[e & FB_LIST_IDX_MASK]), (unsigned)i);
-            start = rpos;
-          }
-        }
-      }
-      const unsigned slot = fb_warp_append(work_n, need);
-      if (need) { a.ray_act[slot] = (unsigned)i; a.ray_act[a.n + slot] = (unsigned)start; }
-    }
-    grid.sync();
-    const unsigned nw = __ldcg(work_n);
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.ctr->ray_work[(round + 2u) % 3u] = 0u;   // next used two barriers from now
-    if (nw == 0u || round >= a.max_rounds) break;
-    if (a.dbg && gt == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_b));
     if (round == 1u) {
       // Contiguous index blocks per warp: neighbouring rays (which share most voxels) are resolved in serial order by one
       // warp, so far fewer optimistic claims have to be taken back in the later rounds.
       const long long per = (a.n + nwarps - 1) / nwarps;
       const long long hi = min((long long)(gw + 1) * per, a.n);
+      unsigned walked = 0;
       for (long long i = (long long)gw * per; i < hi; ++i) {
         if (a.ray_len[i] <= 0) continue;
         const int result = fb_walk_ray(a, (unsigned)i, lane, 0);
         if (lane == 0) a.ray_reach[i] = result;
+        ++walked;
       }
+      if (lane == 0 && walked) atomicAdd(work_n, walked);
     } else {
-      for (unsigned p = gw; p < nw; p += nwarps) {
-        const unsigned i = __ldcg(&a.ray_act[p]);
-        const int result = fb_walk_ray(a, i, lane, (int)__ldcg(&a.ray_act[a.n + p]));
-        if (lane == 0) a.ray_reach[i] = result;
+      // ray of (warp, lane) = gw + lane * nwarps: the rays a lower ray displaces are its index neighbours, which land in
+      // different warps and are walked concurrently
+      for (long long base = 0; base < a.n; base += (long long)nwarps * 32) {
+        const long long i = base + (long long)lane * nwarps + gw;
+        bool need = false;
+        int start = 0;
+        if (i < a.n) {
+          const int L = a.ray_len[i];
+          if (L > 0) {
+            unsigned dp = a.ray_dirty[i];                     // lowest position a lower ray displaced this one from
+            if (dp != FB_RAY_CLEAN) dp = atomicExch(&a.ray_dirty[i], FB_RAY_CLEAN);   // (a concurrent mark must not get lost)
+            const int rr = a.ray_reach[i], rpos = rr & ~FB_REACH_BLOCKED;
+            if (dp < (unsigned)rpos) { need = true; start = (int)dp; }   // (a displaced claim beyond the reach was stale anyway)
+            else if (rr & FB_REACH_BLOCKED) {
+              const unsigned e = __ldcg(&a.ray_list[i * a.cap + (L - 1 - rpos)]);
+              need = !fb_claim_blocks(a, __ldcg(&claims[e & FB_LIST_IDX_MASK]), (unsigned)i);
+              start = rpos;
+            }
+          }
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, need);
+        if (lane == 0 && bal) atomicAdd(work_n, (unsigned)__popc(bal));
+        while (bal) {
+          const int src = __ffs(bal) - 1;
+          bal &= bal - 1u;
+          const unsigned wi = (unsigned)__shfl_sync(0xffffffffu, (int)i, src);
+          const int ws = __shfl_sync(0xffffffffu, start, src);
+          const int result = fb_walk_ray(a, wi, lane, ws);
+          if (lane == 0) a.ray_reach[wi] = result;
+        }
       }
     }
     grid.sync();
+    const unsigned nw = __ldcg(work_n);
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.ctr->ray_work[(round + 2u) % 3u] = 0u;   // next used two barriers from now
     if (a.dbg && gt == 0 && round < 300u) {
       unsigned long long t_c; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_c));
-      a.dbg[3 * round] = nw; a.dbg[3 * round + 1] = t_b - t_a; a.dbg[3 * round + 2] = t_c - t_b;
+      a.dbg[3 * round] = nw; a.dbg[3 * round + 1] = 0; a.dbg[3 * round + 2] = t_c - t_a;
     }
+    if (nw == 0u || round >= a.max_rounds) break;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.ctr->ray_rounds = round;
