@@ -120,13 +120,20 @@ __device__ __forceinline__ void tma_load_box(void *dst, const CUtensorMap *tmap,
 
 #define WF_THREADS 256     // a thread owns 2 voxels (x and x+4) of the tile; four CTAs = four independent tile pipelines per SM
 
-__global__ void __launch_bounds__(WF_THREADS, 4)
+#ifndef WF_GROUP
+#define WF_GROUP 2          // lanes that share the evaluation of one listed voxel (1, 2, 4 or 8)
+#endif
+#ifndef WF_CTAS
+#define WF_CTAS 4           // resident CTAs per SM the register budget is sized for
+#endif
+__global__ void __launch_bounds__(WF_THREADS, WF_CTAS)
 k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
   // buf[0], buf[1]: TMA landing buffers (tile k in buf[k&1], tile k+1 prefetched into the other); a tile is relaxed in place
   __shared__ __align__(128) uint32_t buf[2][FB_BOX_WORDS];
   __shared__ __align__(8) uint64_t mbar[2];
   __shared__ int s_bbox[6];
-  __shared__ unsigned s_next[3];            // {work index, tile id, 1 = needs a full visit} of the prefetched item
+  __shared__ unsigned s_next[6];            // {work index, tile id, 1 = needs a full visit, tile x, y, z} of the prefetched item
+  __shared__ uint32_t s_inner[FB_BOX * FB_BOX];   // per z-row: bits that belong to the halo (all of them for a halo row)
   // per z-row bit masks of the FRESH flags (bit = box z index): a voxel finds out with 13 loads which of its 24 neighbours
   // are in the queue.  fm_halo keeps the (constant) halo bits, fm additionally the interior voxels changed last iteration.
   __shared__ uint32_t fm[FB_BOX * FB_BOX], fm_halo[FB_BOX * FB_BOX];
@@ -155,6 +162,11 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
   for (int k = 0; k < 24; ++k)
     if (tid == k) s_koff[k] = kd[k][0] * (FB_BOX * FB_BOXZ) + kd[k][1] * FB_BOXZ + kd[k][2];
 
+  if (tid < FB_BOX * FB_BOX) {
+    const int rx = tid / FB_BOX, ry = tid % FB_BOX;
+    const bool inner = rx >= FB_HALO && rx < FB_HALO + FB_TILE && ry >= FB_HALO && ry < FB_HALO + FB_TILE;
+    s_inner[tid] = inner ? ~(0xffu << FB_ZPAD) : 0xffffffffu;
+  }
   if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
   __syncthreads();
   unsigned parity[2] = {0u, 0u};
@@ -177,16 +189,17 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
     auto fetch = [&](int slot) {
       const unsigned w = atomicAdd(&a.ctr->next_work[par], 1u);
       unsigned tile = 0, full = 0;
+      int tzc = 0, tyc = 0, txc = 0;
       if (w < nwork) {
         tile = ld_cg_u32(&a.list[cur][w]);
         full = ld_cg_u32(&a.nb_flag[tile]) == stamp_cur ? 1u : 0u;
+        tzc = tile % g.tz; tyc = (tile / g.tz) % g.ty; txc = tile / (g.tz * g.ty);
         if (full) {
-          const int tzc = tile % g.tz, tyc = (tile / g.tz) % g.ty, txc = tile / (g.tz * g.ty);
           mbar_expect_tx(&mbar[slot], FB_BOX_WORDS * 4);
           tma_load_box(buf[slot], &tmap, tzc * FB_TILE - FB_ZPAD, tyc * FB_TILE - FB_HALO, txc * FB_TILE - FB_HALO, &mbar[slot]);
         }
       }
-      s_next[0] = w; s_next[1] = tile; s_next[2] = full;
+      s_next[0] = w; s_next[1] = tile; s_next[2] = full; s_next[3] = (unsigned)txc; s_next[4] = (unsigned)tyc; s_next[5] = (unsigned)tzc;
     };
 
     // ---------------- phase 1: relax every active tile against the previous generation
@@ -195,6 +208,7 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
     __syncthreads();
     for (;;) {
       const unsigned w = s_next[0], tile = s_next[1], full = s_next[2];
+      const int txc = (int)s_next[3], tyc = (int)s_next[4], tzc = (int)s_next[5];   // (three divisions by run-time values, done once)
       __syncthreads();
       if (w >= nwork) break;
       if (tid == 0) {
@@ -202,7 +216,6 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
         s_bbox[0] = s_bbox[2] = s_bbox[4] = 8; s_bbox[1] = s_bbox[3] = s_bbox[5] = -1;
         ++my_visits;
       }
-      const int tzc = tile % g.tz, tyc = (tile / g.tz) % g.ty, txc = tile / (g.tz * g.ty);
       const int x0 = txc * FB_TILE, y0 = tyc * FB_TILE, z0 = tzc * FB_TILE;
       const int vy = y0 + ly, vz = z0 + lz;
       if (!full) {
@@ -226,14 +239,15 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
       mbar_wait(&mbar[slot], parity[slot]);
       parity[slot] ^= 1u;
       uint32_t *V = buf[slot];
-      if (tid < FB_BOX * FB_BOX) {                            // FRESH mask of every z-row of the box
-        uint32_t mk = 0;
-#pragma unroll
-        for (int z = 0; z < FB_BOXZ; ++z) mk |= (V[tid * FB_BOXZ + z] >> 31) << z;
-        const int rx = tid / FB_BOX, ry = tid % FB_BOX;
-        const bool inner = rx >= FB_HALO && rx < FB_HALO + FB_TILE && ry >= FB_HALO && ry < FB_HALO + FB_TILE;
-        fm[tid] = mk;
-        fm_halo[tid] = inner ? (mk & ~(0xffu << FB_ZPAD)) : mk;
+      // FRESH mask of every z-row of the box: a warp reads 32 consecutive words (two rows, conflict free) and votes
+      for (int w0 = (tid >> 5) * 32; w0 < FB_BOX_WORDS; w0 += WF_THREADS) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, (V[w0 + (tid & 31)] >> 31) != 0u);
+        if ((tid & 31) < 2) {
+          const int row = (w0 >> 4) + (tid & 31);
+          const uint32_t mk = (bal >> (16 * (tid & 31))) & 0xffffu;
+          fm[row] = mk;
+          fm_halo[row] = mk & s_inner[row];
+        }
       }
       if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
       uint32_t orig[2], mine[2], nmask[2];
@@ -261,8 +275,8 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
       __syncthreads();
       // Local Jacobi iterations.  (A) every thread derives, for its two voxels, the set of neighbours whose value it has to
       // look at -- the ones in the queue (their push, ESDFMap.cpp:375-391) or all of them when the voxel itself pulls --
-      // and lists the voxel if that set is not empty; (B) the listed voxels are evaluated by groups of four lanes (six
-      // directions each, only the set bits), which turns the sparse, clustered activity of a wave front into dense work for
+      // and lists the voxel if that set is not empty; (B) the listed voxels are evaluated by WF_GROUP lanes each (every
+      // lane its share of the directions, only the set bits), which turns the sparse, clustered activity of a wave front into dense work for
       // all warps; (C) the improvements are applied and become the queue of the next iteration.
       for (int it = 0;; ++it) {
         const int par2 = it & 1;
@@ -302,9 +316,11 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
         if (tid == 0) s_cnt[par2 ^ 1] = 0;
         int anych = 0;
         {
-          const int lane = tid & 31, sub = lane & 3;
-          for (int e0 = (tid >> 5) * 8; e0 < n; e0 += (WF_THREADS / 32) * 8) {
-            const int e = e0 + (lane >> 2);
+          constexpr int GE = 32 / WF_GROUP;                   // listed voxels per warp pass
+          constexpr uint32_t slice0 = WF_GROUP == 1 ? 0xffffffu : WF_GROUP == 2 ? 0x555555u : WF_GROUP == 4 ? 0x111111u : 0x010101u;
+          const int lane = tid & 31, sub = lane % WF_GROUP;
+          for (int e0 = (tid >> 5) * GE; e0 < n; e0 += (WF_THREADS / 32) * GE) {
+            const int e = e0 + lane / WF_GROUP;
             const bool valid = e < n;
             uint32_t self = 0, best = 0, m = 0;
             unsigned bestd = 0xffffffffu;
@@ -317,7 +333,7 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
               self = V[sidx] & FB_CODE_MASK;
               best = self;
               if (best >= 2u) { int ox, oy, oz; fb_unpack(best, ox, oy, oz); ox -= vx; oy -= wy; oz -= wz; bestd = (unsigned)(ox * ox + oy * oy + oz * oz); }
-              m = listF[e] & (0x111111u << sub);
+              m = listF[e] & (slice0 << sub);
             }
             while (m) {
               const int k = __ffs(m) - 1;
@@ -330,7 +346,7 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
               }
             }
 #pragma unroll
-            for (int off = 1; off <= 2; off <<= 1) {
+            for (int off = 1; off < WF_GROUP; off <<= 1) {
               const unsigned od = __shfl_xor_sync(0xffffffffu, bestd, off);
               const uint32_t oc = __shfl_xor_sync(0xffffffffu, best, off);
               if (od < bestd || (od == bestd && oc < best)) { bestd = od; best = oc; }
@@ -405,12 +421,9 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
     if (blockIdx.x == 0 && tid == 0) a.ctr->n_list[cur] = 0;    // consumed; becomes the append target two phases from now
     const unsigned nchg = ld_cg_u32(&a.ctr->n_changed[par]);
     const unsigned stamp = stamp0 + gen + 1u;
-    for (;;) {
-      if (tid == 0) s_next[0] = atomicAdd(&a.ctr->next_work[2u + par], 1u);
-      __syncthreads();
-      const unsigned w = s_next[0];
-      __syncthreads();
-      if (w >= nchg) break;
+    // (uniform items -- one 8^3 copy + <= 19 activations -- so a static stride needs no counter and no block barrier, and the
+    // warps of a CTA run ahead of each other through the dependent loads)
+    for (unsigned w = blockIdx.x; w < nchg; w += gridDim.x) {
       const unsigned tile = ld_cg_u32(&a.changed[par][w]);
       const unsigned bb = ld_cg_u32(&a.changed_bbox[par][w]);
       const int tzc = tile % g.tz, tyc = (tile / g.tz) % g.ty, txc = tile / (g.tz * g.ty);
