@@ -18,7 +18,8 @@
 // still +10000 stays so until a popped neighbour pushes to it (ESDFMap.cpp:375-391) or it is popped itself and pulls
 // (:349-367).  Bit 31 of a record (FB_FRESH) marks "changed in the previous generation / local iteration" = "is in the
 // update queue": a voxel takes candidates from FRESH neighbours (their push) and, when FRESH itself, from all neighbours
-// (its own pull).  Nothing else is relaxed, so unreached voxels stay unreached exactly like in the reference.
+// (its own pull; skipped where it provably finds nothing, see `pulls` below).  Nothing else is relaxed, so unreached voxels
+// stay unreached exactly like in the reference.
 // Tie-break: the reference keeps the first arrival in FIFO order (ESDFMap.cpp:357,382); a parallel wave has no such
 // order, so exact distance ties go to the smallest packed obstacle coordinate (x, then y, then z).
 #include <cooperative_groups.h>

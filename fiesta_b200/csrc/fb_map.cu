@@ -733,14 +733,8 @@ int fiesta_update_esdf(fiesta_map *m) {
   m->st.voxels_changed = (int64_t)m->h_ctr->voxels_changed; m->st.voxels_reset = (int64_t)m->h_ctr->voxels_reset;
   m->st.tile_visits = (int64_t)m->h_ctr->tile_visits; m->st.generations = m->h_ctr->generations;
   if (a.dbg) {
-    unsigned long long h[2048];
+    unsigned long long h[1024];
     CK(cudaMemcpy(h, m->d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
-    if (h[1024 + 4] || h[1024 + 5]) {                      // only filled by a build with FB_WF_PROFILE
-      const unsigned long long *q = h + 1024;
-      const double nf = q[4] ? (double)q[4] : 1.0, nr = q[5] ? (double)q[5] : 1.0;
-      fprintf(stderr, "[wfprof] full %llu (cycles/visit: pre %.0f iterate %.0f epilogue %.0f; iterations %.2f entries/iter %.1f) retire-only %llu (%.0f cycles)\n",
-              q[4], q[0] / nf, q[1] / nf, q[2] / nf, q[6] / nf, q[6] ? (double)q[7] / (double)q[6] : 0.0, q[5], q[3] / nr);
-    }
     fprintf(stderr, "[wf] gens=%u", m->h_ctr->generations);
     for (unsigned gI = 0; gI < m->h_ctr->generations && gI < 256; ++gI) fprintf(stderr, " | %llu/%llu %.0f+%.0fus", h[4 * gI], h[4 * gI + 1], h[4 * gI + 2] * 1e-3, h[4 * gI + 3] * 1e-3);
     fprintf(stderr, "\n");

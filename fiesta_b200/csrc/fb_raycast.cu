@@ -15,14 +15,16 @@
 //                     must round exactly like the reference): Amanatides-Woo traversal with the reference's quirks
 //                     (direction from integer voxel deltas, tie order z>y>x, corner-based distance cut); every pushed voxel
 //                     is classified (count / skip / stop / stamp-only) and stored in the ray's row.
-//   k_ray_resolve   : persistent cooperative kernel, event driven, one WARP per walking ray.  Every voxel holds a claim word {ray, position in
-//                     that ray's list}; a claim is VALID while position < the claiming ray's current reach.  In a round every
-//                     not-yet-final ray walks its list from the far end 32 voxels at a time, stops at the first voxel validly
+//   k_ray_resolve   : persistent cooperative kernel, event driven, one WARP per walking ray.  Every voxel holds a claim
+//                     word {ray, position in that ray's list}; a claim is VALID while position < the claiming ray's current
+//                     reach.  A ray walks its list from the far end 32 voxels at a time, stops at the first voxel validly
 //                     claimed by a LOWER ray index and claims (atomicCAS) what it passes.  Claims are updated in place, so
-//                     higher rays see what lower rays did; a ray that displaces a higher ray's claim marks it dirty.  After
-//                     the first full pass a ray walks again only if it is dirty or the claim that stopped it became
-//                     invalid -- otherwise its walk would give the same result.  A ray only depends on lower indices, so by
-//                     induction the only state in which no ray has to walk is the serial result.  A last walk adds the counts.
+//                     higher rays see what lower rays did; a ray that displaces a higher ray's claim records the position
+//                     (atomicMin).  Round 1 walks every ray (contiguous index blocks per warp); afterwards a ray walks again
+//                     only if it was displaced (resuming at that position) or the claim that stopped it became invalid
+//                     (resuming there) -- otherwise its walk would give the same result.  One grid barrier per round.  A
+//                     ray only depends on lower indices, so by induction the only state in which no ray has to walk is the
+//                     serial result.  A last pass adds the counts.
 // All fp64 arithmetic is written in the reference's operation order and the library is compiled with -fmad=false.
 #include <cooperative_groups.h>
 #include "fb_common.cuh"
