@@ -124,6 +124,9 @@ __device__ __forceinline__ void tma_load_box(void *dst, const CUtensorMap *tmap,
 #ifndef WF_GROUP
 #define WF_GROUP 2          // lanes that share the evaluation of one listed voxel (1, 2, 4 or 8)
 #endif
+#ifndef WF_EXIT_TEST
+#define WF_EXIT_TEST 0        // 1: a visiting tile checks whether its changes can improve a neighbour's border before queueing it
+#endif
 #ifndef WF_CTAS
 #define WF_CTAS 4           // resident CTAs per SM the register budget is sized for
 #endif
@@ -143,6 +146,10 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
   __shared__ uint32_t listF[FB_TILE * FB_TILE * FB_TILE], res[FB_TILE * FB_TILE * FB_TILE];
   __shared__ unsigned s_cnt[2];
   __shared__ int s_koff[24];
+#if WF_EXIT_TEST
+  __shared__ uint32_t cm[FB_BOX * FB_BOX];   // per z-row: records changed by this visit (halo rows stay 0)
+  __shared__ unsigned s_need;                // neighbour directions ((ox+1)*9 + (oy+1)*3 + (oz+1)) whose border would improve
+#endif
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   const int ly = (tid >> 3) & 7, lz = tid & 7;
@@ -163,6 +170,9 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
   for (int k = 0; k < 24; ++k)
     if (tid == k) s_koff[k] = kd[k][0] * (FB_BOX * FB_BOXZ) + kd[k][1] * FB_BOXZ + kd[k][2];
 
+#if WF_EXIT_TEST
+  if (tid < FB_BOX * FB_BOX) cm[tid] = 0u;
+#endif
   if (tid < FB_BOX * FB_BOX) {
     const int rx = tid / FB_BOX, ry = tid % FB_BOX;
     const bool inner = rx >= FB_HALO && rx < FB_HALO + FB_TILE && ry >= FB_HALO && ry < FB_HALO + FB_TILE;
@@ -388,7 +398,17 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
           atomicMin(&s_bbox[4], lz); atomicMax(&s_bbox[5], lz);
         }
         diff = diff || outw[h] != orig[h];
+#if WF_EXIT_TEST
+        {
+          const uint32_t bc = __ballot_sync(0xffffffffu, changed);
+          const int lane = tid & 31;
+          if (lane < 4) cm[(lxh[h] + FB_HALO) * FB_BOX + (((tid >> 5) & 1) * 4 + lane + FB_HALO)] = ((bc >> (8 * lane)) & 0xffu) << FB_ZPAD;
+        }
+#endif
       }
+#if WF_EXIT_TEST
+      if (tid == 0) s_need = 0u;
+#endif
       const int nchanged = __syncthreads_count(nch > 0) ;      // threads with a change (exact voxel count accumulated below)
       const int dirty = __syncthreads_or(diff);               // also true when only stale FRESH flags must be retired
       if (dirty) {
@@ -402,6 +422,75 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
         const unsigned c2 = __reduce_add_sync(0xffffffffu, (unsigned)nch);     // exact number of changed voxels, per warp
         if ((tid & 31) == 0 && c2) atomicAdd(&a.ctr->voxels_changed, (unsigned long long)c2);
       }
+#if WF_EXIT_TEST
+      // Exit test.  Next generation only the records changed here are in the queue; the halo of this box holds the
+      // neighbours' current border values, records only improve, and a neighbour voxel that is queued itself gets its tile
+      // visited anyway.  So a neighbour has to be queued for the sake of THIS tile iff one of its border voxels would take
+      // a candidate from one of the changed records -- decided here exactly, one thread per z-row of the box.
+      unsigned need27 = 0;
+      if (nchanged) {
+        if (tid < FB_BOX * FB_BOX) {
+          const int rx = tid / FB_BOX, ry = tid % FB_BOX;
+          auto cmr = [&](int x, int y) -> uint32_t {
+            return (x >= FB_HALO && x < FB_HALO + FB_TILE && y >= FB_HALO && y < FB_HALO + FB_TILE) ? cm[x * FB_BOX + y] : 0u;
+          };
+          const uint32_t m0 = cmr(rx, ry);
+          const uint32_t f4 = cmr(rx - 1, ry) | cmr(rx + 1, ry) | cmr(rx, ry - 1) | cmr(rx, ry + 1);
+          uint32_t act = (m0 << 1) | (m0 >> 1) | (m0 << 2) | (m0 >> 2) | f4 | (f4 << 1) | (f4 >> 1) |
+                         cmr(rx - 1, ry - 1) | cmr(rx - 1, ry + 1) | cmr(rx + 1, ry - 1) | cmr(rx + 1, ry + 1) |
+                         cmr(rx - 2, ry) | cmr(rx + 2, ry) | cmr(rx, ry - 2) | cmr(rx, ry + 2);
+          const bool inner = rx >= FB_HALO && rx < FB_HALO + FB_TILE && ry >= FB_HALO && ry < FB_HALO + FB_TILE;
+          act &= inner ? (0x3ffcu & ~(0xffu << FB_ZPAD)) : 0x3ffcu;          // halo voxels within reach: box z 2..13
+          const int ox = rx < FB_HALO ? -1 : rx >= FB_HALO + FB_TILE ? 1 : 0, oy = ry < FB_HALO ? -1 : ry >= FB_HALO + FB_TILE ? 1 : 0;
+          while (act) {
+            const int zb = __ffs(act) - 1;
+            act &= act - 1u;
+            const int oz = zb < FB_ZPAD ? -1 : zb >= FB_ZPAD + FB_TILE ? 1 : 0;
+            const unsigned dbit = 1u << ((ox + 1) * 9 + (oy + 1) * 3 + (oz + 1));
+            const uint32_t cy = V[tid * FB_BOXZ + zb] & FB_CODE_MASK;
+            const int x = x0 - FB_HALO + rx, y = y0 - FB_HALO + ry, z = z0 - FB_ZPAD + zb;
+            if (cy == FB_UNKNOWN || !fb_in_range(g, x, y, z)) continue;      // (outside the grid: zero fill = unknown)
+            unsigned dy = 0xffffffffu;
+            if (cy >= 2u) { int px, py, pz; fb_unpack(cy, px, py, pz); px -= x; py -= y; pz -= z; dy = (unsigned)(px * px + py * py + pz * pz); }
+            bool improves = false;
+#pragma unroll
+            for (int k = 0; k < 24; ++k) {
+              const int nx = rx + kd[k][0], ny = ry + kd[k][1], nzb = zb + kd[k][2];
+              if (nx < FB_HALO || nx >= FB_HALO + FB_TILE || ny < FB_HALO || ny >= FB_HALO + FB_TILE || nzb < FB_ZPAD || nzb >= FB_ZPAD + FB_TILE) continue;
+              if (!((cm[nx * FB_BOX + ny] >> nzb) & 1u)) continue;
+              const uint32_t c = V[(nx * FB_BOX + ny) * FB_BOXZ + nzb] & FB_CODE_MASK;
+              if (c >= 2u && c != cy) {
+                int px, py, pz; fb_unpack(c, px, py, pz); px -= x; py -= y; pz -= z;
+                const unsigned d = (unsigned)(px * px + py * py + pz * pz);
+                if (d < dy || (d == dy && c < cy)) improves = true;
+              }
+            }
+            if (improves) atomicOr(&s_need, dbit);
+          }
+        }
+        __syncthreads();
+        if (tid < 32) {                                        // the bounding-box rule stays a necessary condition
+          bool ok = false;
+          if (tid < 27) {
+            const int ox = tid / 9 - 1, oy = (tid / 3) % 3 - 1, oz = tid % 3 - 1;
+            const int nz = (ox != 0) + (oy != 0) + (oz != 0);
+            ok = (nz == 1 || nz == 2) && ((s_need >> tid) & 1u);
+            if (ox < 0) ok = ok && (s_bbox[0] < 2);
+            if (ox > 0) ok = ok && (s_bbox[1] > 5);
+            if (oy < 0) ok = ok && (s_bbox[2] < 2);
+            if (oy > 0) ok = ok && (s_bbox[3] > 5);
+            if (oz < 0) ok = ok && (s_bbox[4] < 2);
+            if (oz > 0) ok = ok && (s_bbox[5] > 5);
+          }
+          need27 = __ballot_sync(0xffffffffu, ok);
+        }
+      }
+      if (tid == 0 && dirty) {
+        const unsigned sl = atomicAdd(&a.ctr->n_changed[par], 1u);
+        a.changed[par][sl] = tile;
+        a.changed_bbox[par][sl] = nchanged ? (need27 | (1u << 31)) : 0u;   // {directions to queue : 27 | some record changed : bit 31}
+      }
+#else
       if (tid == 0 && dirty) {
         const unsigned sl = atomicAdd(&a.ctr->n_changed[par], 1u);
         a.changed[par][sl] = tile;
@@ -409,6 +498,7 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
                                               ((unsigned)s_bbox[3] << 9) | ((unsigned)s_bbox[4] << 12) | ((unsigned)s_bbox[5] << 15) | (1u << 18))
                                            : 0u;
       }
+#endif
       // generic-proxy accesses to buf[slot] must be ordered before the async-proxy (TMA) write of a later prefetch into it
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
@@ -437,6 +527,18 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
           a.cobs[ii] = __ldcg(&a.cobs_b[ii]);
         }
       }
+#if WF_EXIT_TEST
+      if (tid < 27 && (bb >> 31)) {                            // some record changed: queue what the exit test asked for
+        const int ox = tid / 9 - 1, oy = (tid / 3) % 3 - 1, oz = tid % 3 - 1;
+        if (tid == 13) fb_activate(a, tile, stamp, (int)(cur ^ 1u), false);   // revisit once more, only to retire the FRESH flags
+        else if ((bb >> tid) & 1u) {
+          const int nx = txc + ox, ny = tyc + oy, nzc = tzc + oz;
+          if (nx >= 0 && nx < g.tx && ny >= 0 && ny < g.ty && nzc >= 0 && nzc < g.tz)
+            fb_activate(a, (unsigned)((nx * g.ty + ny) * g.tz + nzc), stamp, (int)(cur ^ 1u), true, (unsigned)(g.ty * g.tz));
+        }
+      }
+    }
+#else
       if (tid < 27 && (bb >> 18)) {                            // some record changed: its new value must reach the neighbours
         const int ox = tid / 9 - 1, oy = (tid / 3) % 3 - 1, oz = tid % 3 - 1;
         const int nz = (ox != 0) + (oy != 0) + (oz != 0);
@@ -453,6 +555,7 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
         }
       }
     }
+#endif
     grid.sync();
     if (a.dbg && blockIdx.x == 0 && tid == 0 && gen < 256u) {
       unsigned long long t_c; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_c));

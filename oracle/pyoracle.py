@@ -242,3 +242,64 @@ def raycast(start, end, mn, mx, kind=None):
     if n < 0:
         return None if n == -1 else "hang"
     return buf[:n].astype(np.int64)
+
+
+class FastModel:
+    """CPU model of the product's FAST-mode UpdateESDF (oracle/fast_model.c).  It is driven with the occupancy state of
+    some other map (the reference build on CPU tests, the GPU map on GPU tests): `update(dist, occ)` takes that map's
+    distance_ / occupancy arrays as they are after UpdateOccupancy and before UpdateESDF."""
+    FULL_PULL = 1
+    EXIT_TEST = 2
+
+    def __init__(self, grid_size, resolution, l_occ):
+        path = os.path.join(_HERE, "_build", "libfiesta_fastmodel.so")
+        if not os.path.exists(path):
+            raise RuntimeError("oracle library missing: %s (run `make -C oracle`)" % path)
+        self._L = C.CDLL(path)
+        self._L.fm_create.restype = C.c_void_p
+        self._L.fm_fresh_left.restype = C.c_longlong
+        self.grid_size = tuple(int(g) for g in grid_size)
+        self.n = int(np.prod(self.grid_size))
+        self.res = float(resolution)
+        self.l_occ = float(l_occ)
+        self._h = C.c_void_p(self._L.fm_create(*[C.c_int(g) for g in self.grid_size]))
+        self._exist = np.zeros(self.n, np.uint8)
+        self._seen = np.zeros(self.n, bool)
+
+    def close(self):
+        if self._h is not None:
+            self._L.fm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_range(self, lo, hi):
+        self._L.fm_set_range(self._h, I3(*[int(x) for x in lo]), I3(*[int(x) for x in hi]))
+
+    def update(self, dist, occ, flags=0):
+        """One UpdateESDF.  dist: distance_ (only `!= -10000` = observed is used), occ: occupancy log-odds."""
+        seen = np.asarray(dist) != -10000.0
+        new = np.flatnonzero(seen & ~self._seen).astype(np.uint32)
+        self._L.fm_observe(self._h, new.ctypes, C.c_longlong(len(new)))
+        self._seen = seen
+        exist = (np.asarray(occ) > self.l_occ).astype(np.uint8)
+        ins = np.flatnonzero((exist == 1) & (self._exist == 0)).astype(np.uint32)
+        have_del = bool(np.any((exist == 0) & (self._exist == 1)))
+        self._exist = exist
+        st = (C.c_longlong * 8)()
+        self._L.fm_update(self._h, exist.ctypes, ins.ctypes, C.c_longlong(len(ins)), C.c_int(int(have_del)), C.c_int(int(flags)), st)
+        keys = ("generations", "full_visits", "retire_visits", "changed", "reset", "activations", "suppressed", "iterations")
+        return dict(zip(keys, [int(x) for x in st]))
+
+    def export(self):
+        cobs = np.empty((self.n, 3), np.int32)
+        dist = np.empty(self.n)
+        self._L.fm_export(self._h, cobs.ctypes, dist.ctypes, C.c_double(self.res))
+        return cobs, dist
+
+    def fresh_left(self):
+        return int(self._L.fm_fresh_left(self._h))
