@@ -126,6 +126,7 @@ __device__ __forceinline__ void tma_load_box(void *dst, const CUtensorMap *tmap,
 #endif
 #ifndef WF_EXIT_TEST
 #define WF_EXIT_TEST 0        // 1: a visiting tile checks whether its changes can improve a neighbour's border before queueing it
+                              // (experimental, DESIGN.md section 8: halves the visits; validate with tests/test_gpu_fast_model.py)
 #endif
 #ifndef WF_CTAS
 #define WF_CTAS 4           // resident CTAs per SM the register budget is sized for
@@ -147,7 +148,9 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
   __shared__ unsigned s_cnt[2];
   __shared__ int s_koff[24];
 #if WF_EXIT_TEST
-  __shared__ uint32_t cm[FB_BOX * FB_BOX];   // per z-row: records changed by this visit (halo rows stay 0)
+  // per z-row: records changed by this visit, in a 16x16 row array with a 2-row zero border (index (rx+2)*16 + (ry+2)) so
+  // that the 13 neighbour rows of any box row can be read without bounds checks; only interior rows are ever written
+  __shared__ uint32_t cmp[16 * 16];
   __shared__ unsigned s_need;                // neighbour directions ((ox+1)*9 + (oy+1)*3 + (oz+1)) whose border would improve
 #endif
   cg::grid_group grid = cg::this_grid();
@@ -171,7 +174,7 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
     if (tid == k) s_koff[k] = kd[k][0] * (FB_BOX * FB_BOXZ) + kd[k][1] * FB_BOXZ + kd[k][2];
 
 #if WF_EXIT_TEST
-  if (tid < FB_BOX * FB_BOX) cm[tid] = 0u;
+  cmp[tid] = 0u;                              // WF_THREADS == 256 == 16 * 16
 #endif
   if (tid < FB_BOX * FB_BOX) {
     const int rx = tid / FB_BOX, ry = tid % FB_BOX;
@@ -402,12 +405,12 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
         {
           const uint32_t bc = __ballot_sync(0xffffffffu, changed);
           const int lane = tid & 31;
-          if (lane < 4) cm[(lxh[h] + FB_HALO) * FB_BOX + (((tid >> 5) & 1) * 4 + lane + FB_HALO)] = ((bc >> (8 * lane)) & 0xffu) << FB_ZPAD;
+          if (lane < 4) cmp[(lxh[h] + FB_HALO + 2) * 16 + (((tid >> 5) & 1) * 4 + lane + FB_HALO + 2)] = ((bc >> (8 * lane)) & 0xffu) << FB_ZPAD;
         }
 #endif
       }
 #if WF_EXIT_TEST
-      if (tid == 0) s_need = 0u;
+      if (tid == 0) { s_need = 0u; s_cnt[0] = 0u; }
 #endif
       const int nchanged = __syncthreads_count(nch > 0) ;      // threads with a change (exact voxel count accumulated below)
       const int dirty = __syncthreads_or(diff);               // also true when only stale FRESH flags must be retired
@@ -429,43 +432,71 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
       // a candidate from one of the changed records -- decided here exactly, one thread per z-row of the box.
       unsigned need27 = 0;
       if (nchanged) {
+        // (X1) one thread per z-row of the box lists the halo voxels that have a changed record among their 24 neighbours
         if (tid < FB_BOX * FB_BOX) {
-          const int rx = tid / FB_BOX, ry = tid % FB_BOX;
-          auto cmr = [&](int x, int y) -> uint32_t {
-            return (x >= FB_HALO && x < FB_HALO + FB_TILE && y >= FB_HALO && y < FB_HALO + FB_TILE) ? cm[x * FB_BOX + y] : 0u;
-          };
-          const uint32_t m0 = cmr(rx, ry);
-          const uint32_t f4 = cmr(rx - 1, ry) | cmr(rx + 1, ry) | cmr(rx, ry - 1) | cmr(rx, ry + 1);
+          const int rx = tid / FB_BOX, ry = tid % FB_BOX, p = (rx + 2) * 16 + (ry + 2);
+          const uint32_t m0 = cmp[p];
+          const uint32_t f4 = cmp[p - 16] | cmp[p + 16] | cmp[p - 1] | cmp[p + 1];
           uint32_t act = (m0 << 1) | (m0 >> 1) | (m0 << 2) | (m0 >> 2) | f4 | (f4 << 1) | (f4 >> 1) |
-                         cmr(rx - 1, ry - 1) | cmr(rx - 1, ry + 1) | cmr(rx + 1, ry - 1) | cmr(rx + 1, ry + 1) |
-                         cmr(rx - 2, ry) | cmr(rx + 2, ry) | cmr(rx, ry - 2) | cmr(rx, ry + 2);
+                         cmp[p - 17] | cmp[p - 15] | cmp[p + 15] | cmp[p + 17] | cmp[p - 32] | cmp[p + 32] | cmp[p - 2] | cmp[p + 2];
           const bool inner = rx >= FB_HALO && rx < FB_HALO + FB_TILE && ry >= FB_HALO && ry < FB_HALO + FB_TILE;
           act &= inner ? (0x3ffcu & ~(0xffu << FB_ZPAD)) : 0x3ffcu;          // halo voxels within reach: box z 2..13
-          const int ox = rx < FB_HALO ? -1 : rx >= FB_HALO + FB_TILE ? 1 : 0, oy = ry < FB_HALO ? -1 : ry >= FB_HALO + FB_TILE ? 1 : 0;
-          while (act) {
-            const int zb = __ffs(act) - 1;
-            act &= act - 1u;
-            const int oz = zb < FB_ZPAD ? -1 : zb >= FB_ZPAD + FB_TILE ? 1 : 0;
-            const unsigned dbit = 1u << ((ox + 1) * 9 + (oy + 1) * 3 + (oz + 1));
-            const uint32_t cy = V[tid * FB_BOXZ + zb] & FB_CODE_MASK;
+          if (act) {
+            const unsigned cnt = (unsigned)__popc(act);
+            unsigned pos = atomicAdd(&s_cnt[0], cnt);
+            if (pos + cnt > (unsigned)(FB_TILE * FB_TILE * FB_TILE)) atomicOr(&s_need, 0x07ffffffu);   // list full: queue as the box rule says
+            else
+              while (act) {
+                const int zb = __ffs(act) - 1;
+                act &= act - 1u;
+                listV[pos++] = (unsigned short)((tid << 4) | zb);
+              }
+          }
+        }
+        __syncthreads();
+        // (X2) the listed voxels are checked like step (B): WF_GROUP lanes each, only against the changed neighbours
+        {
+          constexpr int GE = 32 / WF_GROUP;
+          constexpr uint32_t slice0 = WF_GROUP == 1 ? 0xffffffu : WF_GROUP == 2 ? 0x555555u : WF_GROUP == 4 ? 0x111111u : 0x010101u;
+          const int lane = tid & 31, sub = lane % WF_GROUP;
+          const int n = s_cnt[0] > (unsigned)(FB_TILE * FB_TILE * FB_TILE) ? 0 : (int)s_cnt[0];   // (overflow: every direction is already asked for)
+          for (int e0 = (tid >> 5) * GE; e0 < n; e0 += (WF_THREADS / 32) * GE) {
+            const int e = e0 + lane / WF_GROUP;
+            if (e >= n) continue;
+            const int v = listV[e];
+            const int row = v >> 4, zb = v & 15, rx = row / FB_BOX, ry = row % FB_BOX, p = (rx + 2) * 16 + (ry + 2);
+            const int sidx = row * FB_BOXZ + zb;
+            const uint32_t cy = V[sidx] & FB_CODE_MASK;
             const int x = x0 - FB_HALO + rx, y = y0 - FB_HALO + ry, z = z0 - FB_ZPAD + zb;
-            if (cy == FB_UNKNOWN || !fb_in_range(g, x, y, z)) continue;      // (outside the grid: zero fill = unknown)
+            if (cy == FB_UNKNOWN || !fb_in_range(g, x, y, z)) continue;      // barrier / outside the box (outside the grid: zero fill)
+            const uint32_t m0 = cmp[p];
+            uint32_t F = ((m0 >> (zb - 2)) & 3u) | (((m0 >> (zb + 1)) & 3u) << 2) |
+                         (((cmp[p - 16] >> (zb - 1)) & 7u) << 4) | (((cmp[p + 16] >> (zb - 1)) & 7u) << 7) |
+                         (((cmp[p - 1] >> (zb - 1)) & 7u) << 10) | (((cmp[p + 1] >> (zb - 1)) & 7u) << 13) |
+                         (((cmp[p - 17] >> zb) & 1u) << 16) | (((cmp[p - 15] >> zb) & 1u) << 17) |
+                         (((cmp[p + 15] >> zb) & 1u) << 18) | (((cmp[p + 17] >> zb) & 1u) << 19) |
+                         (((cmp[p - 32] >> zb) & 1u) << 20) | (((cmp[p + 32] >> zb) & 1u) << 21) |
+                         (((cmp[p - 2] >> zb) & 1u) << 22) | (((cmp[p + 2] >> zb) & 1u) << 23);
+            uint32_t m = F & (slice0 << sub);
+            if (!m) continue;
             unsigned dy = 0xffffffffu;
             if (cy >= 2u) { int px, py, pz; fb_unpack(cy, px, py, pz); px -= x; py -= y; pz -= z; dy = (unsigned)(px * px + py * py + pz * pz); }
             bool improves = false;
-#pragma unroll
-            for (int k = 0; k < 24; ++k) {
-              const int nx = rx + kd[k][0], ny = ry + kd[k][1], nzb = zb + kd[k][2];
-              if (nx < FB_HALO || nx >= FB_HALO + FB_TILE || ny < FB_HALO || ny >= FB_HALO + FB_TILE || nzb < FB_ZPAD || nzb >= FB_ZPAD + FB_TILE) continue;
-              if (!((cm[nx * FB_BOX + ny] >> nzb) & 1u)) continue;
-              const uint32_t c = V[(nx * FB_BOX + ny) * FB_BOXZ + nzb] & FB_CODE_MASK;
+            while (m) {
+              const int k = __ffs(m) - 1;
+              m &= m - 1u;
+              const uint32_t c = V[sidx + s_koff[k]] & FB_CODE_MASK;       // a changed record of this tile (interior: in bounds)
               if (c >= 2u && c != cy) {
                 int px, py, pz; fb_unpack(c, px, py, pz); px -= x; py -= y; pz -= z;
                 const unsigned d = (unsigned)(px * px + py * py + pz * pz);
-                if (d < dy || (d == dy && c < cy)) improves = true;
+                improves = improves || d < dy || (d == dy && c < cy);
               }
             }
-            if (improves) atomicOr(&s_need, dbit);
+            if (improves) {
+              const int ox = rx < FB_HALO ? -1 : rx >= FB_HALO + FB_TILE ? 1 : 0, oy = ry < FB_HALO ? -1 : ry >= FB_HALO + FB_TILE ? 1 : 0;
+              const int oz = zb < FB_ZPAD ? -1 : zb >= FB_ZPAD + FB_TILE ? 1 : 0;
+              atomicOr(&s_need, 1u << ((ox + 1) * 9 + (oy + 1) * 3 + (oz + 1)));
+            }
           }
         }
         __syncthreads();
