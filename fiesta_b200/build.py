@@ -38,7 +38,9 @@ def build(force=False, verbose=False):
         s = os.path.join(CSRC, src)
         o = os.path.join(LIBDIR, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + hdrs):
-            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            # FIESTA_B200_NVCC_FLAGS: extra flags for experiments, e.g. "-DWF_EXIT_TEST=1" (use together with --force)
+            extra = os.environ.get("FIESTA_B200_NVCC_FLAGS", "").split()
+            cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             subprocess.check_call(cmd)
         objs.append(o)
     if force or _stale(LIB, objs):
