@@ -9,6 +9,7 @@
  *       with the strict-improvement rule, unknown-voxel barriers, FRESH = "is in the queue" frontier semantics, ties to
  *       the smallest packed obstacle coordinate, Jacobi between tiles (a generation only reads the previous one), bounding
  *       box driven neighbour activation, flag-retire visits                                    (k_wavefront)
+ * (Tiles are 8^3 like the kernels'; fm_create_tiled(.., 16) exists only to study a 16^3 variant offline.)
  * The GPU result does not depend on thread or CTA scheduling, so the kernels must reproduce this model bit for bit
  * (tests/test_gpu_fast_model.py); the model itself is checked against the reference build on CPU (tests/test_fast_model.py).
  * Two switches exist to study variants offline: FM_FULL_PULL (every queued voxel pulls, the literal reading of
@@ -31,6 +32,7 @@
 
 typedef struct fm {
   int gx, gy, gz, tx, ty, tz;
+  int T, lg;                   /* tile edge (8 like the kernels; 16 for offline studies) and its log2 */
   long long total;
   int lo[3], hi[3];            /* update box, inclusive (ESDFMap::VoxInRange, ESDFMap.cpp:63-72) */
   uint32_t *code, *stage;      /* records {0 unknown | 1 no obstacle | packed obstacle} + FRESH bit; staging copy */
@@ -61,11 +63,12 @@ static unsigned dist2(uint32_t c, int x, int y, int z) {
   return (unsigned)(ox * ox + oy * oy + oz * oz);
 }
 
-fm *fm_create(int gx, int gy, int gz) {
+fm *fm_create_tiled(int gx, int gy, int gz, int tile) {
   fm *m = (fm *)calloc(1, sizeof(fm));
-  if (!m) return NULL;
+  if (!m || (tile != 8 && tile != 16)) { free(m); return NULL; }
   m->gx = gx; m->gy = gy; m->gz = gz;
-  m->tx = (gx + 7) / 8; m->ty = (gy + 7) / 8; m->tz = (gz + 7) / 8;
+  m->T = tile; m->lg = tile == 8 ? 3 : 4;
+  m->tx = (gx + tile - 1) / tile; m->ty = (gy + tile - 1) / tile; m->tz = (gz + tile - 1) / tile;
   m->total = (long long)gx * gy * gz;
   const size_t nt = (size_t)m->tx * m->ty * m->tz;
   m->code = (uint32_t *)calloc((size_t)m->total, 4);
@@ -82,6 +85,7 @@ fm *fm_create(int gx, int gy, int gz) {
   m->stamp = 1;
   return m;
 }
+fm *fm_create(int gx, int gy, int gz) { return fm_create_tiled(gx, gy, gz, 8); }
 void fm_destroy(fm *m) {
   if (!m) return;
   free(m->code); free(m->stage); free(m->tile_flag); free(m->nb_flag); free(m->list[0]); free(m->list[1]);
@@ -102,14 +106,18 @@ static void activate(fm *m, unsigned t, unsigned stamp, int which, int work) {
   if (m->tile_flag[t] != stamp) { m->tile_flag[t] = stamp; m->list[which][m->n_list[which]++] = t; }
 }
 
-#define BOX 12
+#define MAXT 16
+#define MAXBOX (MAXT + 4)
 #define BIDX(bx, by, bz) (((bx) * BOX + (by)) * BOX + (bz))
+#define VIDX(lx, ly, lz) (((lx) * T + (ly)) * T + (lz))
 
 /* stats: 0 generations, 1 full visits, 2 retire-only visits, 3 changed records, 4 reset records, 5 neighbour activations
- * asked for by the bounding-box rule, 6 of those suppressed by the exit test, 7 local iterations */
+ * asked for by the bounding-box rule, 6 of those suppressed by the exit test, 7 local iterations, 8 voxel evaluations
+ * (listed voxels summed over the iterations), 9 candidate records compared */
 void fm_update(fm *m, const uint8_t *exist, const uint32_t *ins, long long n_ins, int have_del, int flags, long long *stats) {
   const int full_box = box_is_full(m);
-  long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int T = m->T, lg = m->lg, BOX = T + 4;
+  long long st[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const unsigned stamp0 = m->stamp;
   m->n_list[0] = m->n_list[1] = 0;
   /* E1 (ESDFMap.cpp:278-291) */
@@ -118,9 +126,9 @@ void fm_update(fm *m, const uint8_t *exist, const uint32_t *ins, long long n_ins
     if (!exist[ii]) continue;
     const int z = (int)(ii % (unsigned)m->gz), y = (int)((ii / (unsigned)m->gz) % (unsigned)m->gy), x = (int)(ii / ((unsigned)m->gz * (unsigned)m->gy));
     m->code[ii] = pack(x, y, z) | FM_FRESH;
-    const int tx0 = (x - 2 > 0 ? x - 2 : 0) >> 3, tx1 = (x + 2 < m->gx - 1 ? x + 2 : m->gx - 1) >> 3;
-    const int ty0 = (y - 2 > 0 ? y - 2 : 0) >> 3, ty1 = (y + 2 < m->gy - 1 ? y + 2 : m->gy - 1) >> 3;
-    const int tz0 = (z - 2 > 0 ? z - 2 : 0) >> 3, tz1 = (z + 2 < m->gz - 1 ? z + 2 : m->gz - 1) >> 3;
+    const int tx0 = (x - 2 > 0 ? x - 2 : 0) >> lg, tx1 = (x + 2 < m->gx - 1 ? x + 2 : m->gx - 1) >> lg;
+    const int ty0 = (y - 2 > 0 ? y - 2 : 0) >> lg, ty1 = (y + 2 < m->gy - 1 ? y + 2 : m->gy - 1) >> lg;
+    const int tz0 = (z - 2 > 0 ? z - 2 : 0) >> lg, tz1 = (z + 2 < m->gz - 1 ? z + 2 : m->gz - 1) >> lg;
     for (int a = tx0; a <= tx1; ++a)
       for (int b = ty0; b <= ty1; ++b)
         for (int c = tz0; c <= tz1; ++c) activate(m, (unsigned)((a * m->ty + b) * m->tz + c), stamp0, 0, 1);
@@ -138,26 +146,26 @@ void fm_update(fm *m, const uint8_t *exist, const uint32_t *ins, long long n_ins
             if (!exist[lin(m, ox, oy, oz)]) {
               m->code[ii] = FM_INF | FM_FRESH;
               ++st[4];
-              activate(m, (unsigned)(((x >> 3) * m->ty + (y >> 3)) * m->tz + (z >> 3)), stamp0, 0, 1);
+              activate(m, (unsigned)(((x >> lg) * m->ty + (y >> lg)) * m->tz + (z >> lg)), stamp0, 0, 1);
             }
           }
         }
   /* E3 */
   unsigned cur = 0, gen = 0;
-  uint32_t V[BOX * BOX * BOX], orig[BOX * BOX * BOX], nv[512];
-  unsigned char fresh[BOX * BOX * BOX], upd[512], pulls[512], chg[BOX * BOX * BOX];
+  static uint32_t V[MAXBOX * MAXBOX * MAXBOX], orig[MAXBOX * MAXBOX * MAXBOX], nv[MAXT * MAXT * MAXT];
+  static unsigned char fresh[MAXBOX * MAXBOX * MAXBOX], upd[MAXT * MAXT * MAXT], pulls[MAXT * MAXT * MAXT], chg[MAXBOX * MAXBOX * MAXBOX];
   while (m->n_list[cur]) {
     const unsigned nwork = m->n_list[cur], stamp_cur = stamp0 + gen;
     m->n_changed = 0;
     for (unsigned w = 0; w < nwork; ++w) {
       const unsigned tile = m->list[cur][w];
       const int tzc = (int)(tile % (unsigned)m->tz), tyc = (int)((tile / (unsigned)m->tz) % (unsigned)m->ty), txc = (int)(tile / ((unsigned)m->tz * (unsigned)m->ty));
-      const int x0 = txc * 8, y0 = tyc * 8, z0 = tzc * 8;
+      const int x0 = txc * T, y0 = tyc * T, z0 = tzc * T;
       if (m->nb_flag[tile] != stamp_cur) {
         /* queued only by itself: retire the FRESH flags (through the staging copy) */
-        for (int lx = 0; lx < 8; ++lx)
-          for (int ly = 0; ly < 8; ++ly)
-            for (int lz = 0; lz < 8; ++lz)
+        for (int lx = 0; lx < T; ++lx)
+          for (int ly = 0; ly < T; ++ly)
+            for (int lz = 0; lz < T; ++lz)
               if (in_grid(m, x0 + lx, y0 + ly, z0 + lz)) { const long long ii = lin(m, x0 + lx, y0 + ly, z0 + lz); m->stage[ii] = m->code[ii] & FM_MASK; }
         m->changed[m->n_changed] = tile; m->changed_bb[m->n_changed] = 0; m->changed_need[m->n_changed] = 0; ++m->n_changed;
         ++st[2];
@@ -171,10 +179,10 @@ void fm_update(fm *m, const uint8_t *exist, const uint32_t *ins, long long n_ins
             const uint32_t c = in_grid(m, x, y, z) ? m->code[lin(m, x, y, z)] : 0u;   /* outside the grid = never observed */
             V[BIDX(bx, by, bz)] = c & FM_MASK; orig[BIDX(bx, by, bz)] = c; fresh[BIDX(bx, by, bz)] = (unsigned char)(c >> 31);
           }
-      for (int lx = 0; lx < 8; ++lx)
-        for (int ly = 0; ly < 8; ++ly)
-          for (int lz = 0; lz < 8; ++lz) {
-            const int v = (lx * 8 + ly) * 8 + lz;
+      for (int lx = 0; lx < T; ++lx)
+        for (int ly = 0; ly < T; ++ly)
+          for (int lz = 0; lz < T; ++lz) {
+            const int v = VIDX(lx, ly, lz);
             const uint32_t c = V[BIDX(lx + 2, ly + 2, lz + 2)];
             /* unknown voxels are barriers (distance_ = -10000 is never > tmp, ESDFMap.cpp:382); only in-box voxels are queued */
             upd[v] = (unsigned char)(c != FM_UNKNOWN && in_range(m, x0 + lx, y0 + ly, z0 + lz));
@@ -183,10 +191,10 @@ void fm_update(fm *m, const uint8_t *exist, const uint32_t *ins, long long n_ins
       for (;;) {                                          /* local Jacobi iterations */
         ++st[7];
         int listed = 0, any = 0;
-        for (int lx = 0; lx < 8; ++lx)
-          for (int ly = 0; ly < 8; ++ly)
-            for (int lz = 0; lz < 8; ++lz) {
-              const int v = (lx * 8 + ly) * 8 + lz, b = BIDX(lx + 2, ly + 2, lz + 2);
+        for (int lx = 0; lx < T; ++lx)
+          for (int ly = 0; ly < T; ++ly)
+            for (int lz = 0; lz < T; ++lz) {
+              const int v = VIDX(lx, ly, lz), b = BIDX(lx + 2, ly + 2, lz + 2);
               nv[v] = V[b];
               if (!upd[v]) continue;
               const int x = x0 + lx, y = y0 + ly, z = z0 + lz;
@@ -199,6 +207,7 @@ void fm_update(fm *m, const uint8_t *exist, const uint32_t *ins, long long n_ins
                 if (!(pull || fresh[nb])) continue;       /* the neighbour's push (ESDFMap.cpp:375-391) or this voxel's pull (:349-367) */
                 if (!in_range(m, x + KD[k][0], y + KD[k][1], z + KD[k][2])) continue;   /* VoxInRange(new_pos), :351 */
                 considered = 1;
+                ++st[9];
                 const uint32_t c = V[nb];
                 if (c >= 2u && c != best) {
                   const unsigned d = dist2(c, x, y, z);
@@ -206,31 +215,32 @@ void fm_update(fm *m, const uint8_t *exist, const uint32_t *ins, long long n_ins
                 }
               }
               listed |= considered;
+              st[8] += considered;
               nv[v] = best;
             }
         if (!listed) break;
-        for (int lx = 0; lx < 8; ++lx)
-          for (int ly = 0; ly < 8; ++ly)
-            for (int lz = 0; lz < 8; ++lz) {
-              const int v = (lx * 8 + ly) * 8 + lz, b = BIDX(lx + 2, ly + 2, lz + 2);
+        for (int lx = 0; lx < T; ++lx)
+          for (int ly = 0; ly < T; ++ly)
+            for (int lz = 0; lz < T; ++lz) {
+              const int v = VIDX(lx, ly, lz), b = BIDX(lx + 2, ly + 2, lz + 2);
               const int c = nv[v] != V[b];
               any |= c;
               chg[b] = (unsigned char)c;
             }
         if (!any) break;
-        for (int lx = 0; lx < 8; ++lx)
-          for (int ly = 0; ly < 8; ++ly)
-            for (int lz = 0; lz < 8; ++lz) {
-              const int v = (lx * 8 + ly) * 8 + lz, b = BIDX(lx + 2, ly + 2, lz + 2);
+        for (int lx = 0; lx < T; ++lx)
+          for (int ly = 0; ly < T; ++ly)
+            for (int lz = 0; lz < T; ++lz) {
+              const int v = VIDX(lx, ly, lz), b = BIDX(lx + 2, ly + 2, lz + 2);
               V[b] = nv[v]; fresh[b] = chg[b];             /* the queue of the next iteration */
             }
       }
       /* epilogue: what changed during this generation is FRESH for the next one */
-      int nch = 0, dirty = 0, bb[6] = {8, -1, 8, -1, 8, -1};
+      int nch = 0, dirty = 0, bb[6] = {T, -1, T, -1, T, -1};
       memset(chg, 0, sizeof(chg));
-      for (int lx = 0; lx < 8; ++lx)
-        for (int ly = 0; ly < 8; ++ly)
-          for (int lz = 0; lz < 8; ++lz) {
+      for (int lx = 0; lx < T; ++lx)
+        for (int ly = 0; ly < T; ++ly)
+          for (int lz = 0; lz < T; ++lz) {
             const int b = BIDX(lx + 2, ly + 2, lz + 2);
             const int changed = V[b] != (orig[b] & FM_MASK);
             const uint32_t outw = V[b] | (changed ? FM_FRESH : 0u);
@@ -243,9 +253,9 @@ void fm_update(fm *m, const uint8_t *exist, const uint32_t *ins, long long n_ins
             if (outw != orig[b]) dirty = 1;
           }
       if (dirty) {
-        for (int lx = 0; lx < 8; ++lx)
-          for (int ly = 0; ly < 8; ++ly)
-            for (int lz = 0; lz < 8; ++lz)
+        for (int lx = 0; lx < T; ++lx)
+          for (int ly = 0; ly < T; ++ly)
+            for (int lz = 0; lz < T; ++lz)
               if (in_grid(m, x0 + lx, y0 + ly, z0 + lz)) {
                 const int b = BIDX(lx + 2, ly + 2, lz + 2);
                 m->stage[lin(m, x0 + lx, y0 + ly, z0 + lz)] = V[b] | (chg[b] ? FM_FRESH : 0u);
@@ -258,7 +268,7 @@ void fm_update(fm *m, const uint8_t *exist, const uint32_t *ins, long long n_ins
           for (int bx = 0; bx < BOX; ++bx)
             for (int by = 0; by < BOX; ++by)
               for (int bz = 0; bz < BOX; ++bz) {
-                const int ox = bx < 2 ? -1 : bx > 9 ? 1 : 0, oy = by < 2 ? -1 : by > 9 ? 1 : 0, oz = bz < 2 ? -1 : bz > 9 ? 1 : 0;
+                const int ox = bx < 2 ? -1 : bx > T + 1 ? 1 : 0, oy = by < 2 ? -1 : by > T + 1 ? 1 : 0, oz = bz < 2 ? -1 : bz > T + 1 ? 1 : 0;
                 if (!ox && !oy && !oz) continue;
                 const int dirbit = ((ox + 1) * 3 + (oy + 1)) * 3 + (oz + 1);
                 if ((need >> dirbit) & 1u) continue;
@@ -268,7 +278,7 @@ void fm_update(fm *m, const uint8_t *exist, const uint32_t *ins, long long n_ins
                 const unsigned dy = cy >= 2u ? dist2(cy, x, y, z) : 0xffffffffu;
                 for (int k = 0; k < 24; ++k) {
                   const int nx = bx + KD[k][0], ny = by + KD[k][1], nz = bz + KD[k][2];
-                  if (nx < 2 || nx > 9 || ny < 2 || ny > 9 || nz < 2 || nz > 9) continue;      /* candidates: this tile's records */
+                  if (nx < 2 || nx > T + 1 || ny < 2 || ny > T + 1 || nz < 2 || nz > T + 1) continue;      /* candidates: this tile's records */
                   if (!chg[BIDX(nx, ny, nz)]) continue;
                   const uint32_t c = V[BIDX(nx, ny, nz)];
                   if (c >= 2u && c != cy) {
@@ -279,8 +289,8 @@ void fm_update(fm *m, const uint8_t *exist, const uint32_t *ins, long long n_ins
               }
         }
         m->changed[m->n_changed] = tile;
-        m->changed_bb[m->n_changed] = nch ? ((unsigned)bb[0] | ((unsigned)bb[1] << 3) | ((unsigned)bb[2] << 6) | ((unsigned)bb[3] << 9) |
-                                             ((unsigned)bb[4] << 12) | ((unsigned)bb[5] << 15) | (1u << 18)) : 0u;
+        m->changed_bb[m->n_changed] = nch ? ((unsigned)bb[0] | ((unsigned)bb[1] << 5) | ((unsigned)bb[2] << 10) | ((unsigned)bb[3] << 15) |
+                                             ((unsigned)bb[4] << 20) | ((unsigned)bb[5] << 25) | (1u << 30)) : 0u;
         m->changed_need[m->n_changed] = need;
         ++m->n_changed;
         st[3] += nch;
@@ -292,12 +302,12 @@ void fm_update(fm *m, const uint8_t *exist, const uint32_t *ins, long long n_ins
     for (unsigned w = 0; w < m->n_changed; ++w) {
       const unsigned tile = m->changed[w], bbw = m->changed_bb[w];
       const int tzc = (int)(tile % (unsigned)m->tz), tyc = (int)((tile / (unsigned)m->tz) % (unsigned)m->ty), txc = (int)(tile / ((unsigned)m->tz * (unsigned)m->ty));
-      for (int lx = 0; lx < 8; ++lx)
-        for (int ly = 0; ly < 8; ++ly)
-          for (int lz = 0; lz < 8; ++lz)
-            if (in_grid(m, txc * 8 + lx, tyc * 8 + ly, tzc * 8 + lz)) { const long long ii = lin(m, txc * 8 + lx, tyc * 8 + ly, tzc * 8 + lz); m->code[ii] = m->stage[ii]; }
-      if (!(bbw >> 18)) continue;
-      const int mnx = bbw & 7, mxx = (bbw >> 3) & 7, mny = (bbw >> 6) & 7, mxy = (bbw >> 9) & 7, mnz = (bbw >> 12) & 7, mxz = (bbw >> 15) & 7;
+      for (int lx = 0; lx < T; ++lx)
+        for (int ly = 0; ly < T; ++ly)
+          for (int lz = 0; lz < T; ++lz)
+            if (in_grid(m, txc * T + lx, tyc * T + ly, tzc * T + lz)) { const long long ii = lin(m, txc * T + lx, tyc * T + ly, tzc * T + lz); m->code[ii] = m->stage[ii]; }
+      if (!(bbw >> 30)) continue;
+      const int mnx = bbw & 31, mxx = (bbw >> 5) & 31, mny = (bbw >> 10) & 31, mxy = (bbw >> 15) & 31, mnz = (bbw >> 20) & 31, mxz = (bbw >> 25) & 31;
       for (int ox = -1; ox <= 1; ++ox)
         for (int oy = -1; oy <= 1; ++oy)
           for (int oz = -1; oz <= 1; ++oz) {
@@ -306,11 +316,11 @@ void fm_update(fm *m, const uint8_t *exist, const uint32_t *ins, long long n_ins
             if (nz != 1 && nz != 2) continue;                                /* no 3-D corner directions in dirs_ */
             int need = 1;
             if (ox < 0) need = need && (mnx < 2);
-            if (ox > 0) need = need && (mxx > 5);
+            if (ox > 0) need = need && (mxx > T - 3);
             if (oy < 0) need = need && (mny < 2);
-            if (oy > 0) need = need && (mxy > 5);
+            if (oy > 0) need = need && (mxy > T - 3);
             if (oz < 0) need = need && (mnz < 2);
-            if (oz > 0) need = need && (mxz > 5);
+            if (oz > 0) need = need && (mxz > T - 3);
             const int ax = txc + ox, ay = tyc + oy, az = tzc + oz;
             if (!(need && ax >= 0 && ax < m->tx && ay >= 0 && ay < m->ty && az >= 0 && az < m->tz)) continue;
             ++st[5];

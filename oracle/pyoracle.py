@@ -251,18 +251,18 @@ class FastModel:
     FULL_PULL = 1
     EXIT_TEST = 2
 
-    def __init__(self, grid_size, resolution, l_occ):
+    def __init__(self, grid_size, resolution, l_occ, tile=8):
         path = os.path.join(_HERE, "_build", "libfiesta_fastmodel.so")
         if not os.path.exists(path):
             raise RuntimeError("oracle library missing: %s (run `make -C oracle`)" % path)
         self._L = C.CDLL(path)
-        self._L.fm_create.restype = C.c_void_p
+        self._L.fm_create_tiled.restype = C.c_void_p
         self._L.fm_fresh_left.restype = C.c_longlong
         self.grid_size = tuple(int(g) for g in grid_size)
         self.n = int(np.prod(self.grid_size))
         self.res = float(resolution)
         self.l_occ = float(l_occ)
-        self._h = C.c_void_p(self._L.fm_create(*[C.c_int(g) for g in self.grid_size]))
+        self._h = C.c_void_p(self._L.fm_create_tiled(*[C.c_int(g) for g in self.grid_size], C.c_int(tile)))
         self._exist = np.zeros(self.n, np.uint8)
         self._seen = np.zeros(self.n, bool)
 
@@ -290,9 +290,10 @@ class FastModel:
         ins = np.flatnonzero((exist == 1) & (self._exist == 0)).astype(np.uint32)
         have_del = bool(np.any((exist == 0) & (self._exist == 1)))
         self._exist = exist
-        st = (C.c_longlong * 8)()
+        st = (C.c_longlong * 10)()
         self._L.fm_update(self._h, exist.ctypes, ins.ctypes, C.c_longlong(len(ins)), C.c_int(int(have_del)), C.c_int(int(flags)), st)
-        keys = ("generations", "full_visits", "retire_visits", "changed", "reset", "activations", "suppressed", "iterations")
+        keys = ("generations", "full_visits", "retire_visits", "changed", "reset", "activations", "suppressed", "iterations",
+                "evaluations", "candidates")
         return dict(zip(keys, [int(x) for x in st]))
 
     def export(self):

@@ -19,7 +19,9 @@ ora = pyoracle.OracleMap(w["origin"], w["res"], w["size"])
 ora.SetParameters(*scenes.PARAMS_DEFAULT)
 l_occ = float(np.log(scenes.PARAMS_DEFAULT[4] / (1 - scenes.PARAMS_DEFAULT[4])))
 base, full, ex = (pyoracle.FastModel(ora.grid_size, ora.resolution, l_occ) for _ in range(3))
+t16, t16x = (pyoracle.FastModel(ora.grid_size, ora.resolution, l_occ, tile=16) for _ in range(2))
 tot = dict(base=0, exit=0, act=0, sup=0)
+agg = {k: dict(generations=0, full_visits=0, iterations=0, evaluations=0, candidates=0, diff=0) for k in ("8", "8x", "16", "16x")}
 for f, (pts, T) in enumerate(frames):
     ora.RaycastFrame(pts, T, w["min_len"], w["max_len"])
     if not ora.CheckUpdate():
@@ -29,6 +31,8 @@ for f, (pts, T) in enumerate(frames):
     s0 = base.update(dist, occ, 0)
     s1 = full.update(dist, occ, pyoracle.FastModel.FULL_PULL)
     s2 = ex.update(dist, occ, pyoracle.FastModel.EXIT_TEST)
+    s3 = t16.update(dist, occ, 0)
+    s4 = t16x.update(dist, occ, pyoracle.FastModel.EXIT_TEST)
     ora.UpdateESDF()
     c0, d0 = base.export(); c1, d1 = full.export(); c2, d2 = ex.export()
     same = np.array_equal(c0, c1) and np.array_equal(c0, c2)
@@ -40,5 +44,14 @@ for f, (pts, T) in enumerate(frames):
              100.0 * (d0 != R)[fin].mean() if fin.any() else 0.0, int(fin.sum())), flush=True)
     assert same and s0["full_visits"] == s1["full_visits"]
     tot["base"] += s0["full_visits"]; tot["exit"] += s2["full_visits"]; tot["act"] += s2["activations"]; tot["sup"] += s2["suppressed"]
+    c3, d3 = t16.export(); c4, d4 = t16x.export()
+    for k, st, dd in (("8", s0, d0), ("8x", s2, d2), ("16", s3, d3), ("16x", s4, d4)):
+        for q in ("generations", "full_visits", "iterations", "evaluations", "candidates"):
+            agg[k][q] += st[q]
+        agg[k]["diff"] += int((dd != d0).sum())
 print("total full visits %d -> %d (%.1f %%), %d of %d neighbour activations suppressed" %
       (tot["base"], tot["exit"], 100.0 * tot["exit"] / max(1, tot["base"]), tot["sup"], tot["act"]))
+print("tile / exit test | generations | full visits | local iterations | voxel evaluations | candidates | distances != 8^3 result")
+for k in ("8", "8x", "16", "16x"):
+    g = agg[k]
+    print("%4s | %6d | %8d | %8d | %10d | %11d | %d" % (k, g["generations"], g["full_visits"], g["iterations"], g["evaluations"], g["candidates"], g["diff"]))
