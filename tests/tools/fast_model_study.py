@@ -1,9 +1,9 @@
 """Offline study with the CPU model of the FAST-mode UpdateESDF (oracle/fast_model.c): how many tile visits does the exit
 test (a visiting tile checks exactly whether its changes can improve a neighbour's border before queueing it) save on the
 LIDAR workload, and does it -- or pulling from every queued voxel -- change any record?  CPU only.
-    python scripts/fast_model_study.py [--workload lidar256] [--frames 12]"""
+    python tests/tools/fast_model_study.py [--workload lidar256] [--frames 12]"""
 import argparse, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import bench
 from oracle import pyoracle
