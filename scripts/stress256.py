@@ -1,7 +1,7 @@
 """Dynamic-obstacle stress (BASELINE.json configs[4]): 256^3 grid, every voxel observed, then every frame a
 uniformly random 20 % of the voxels is toggled occupied <-> free (toggle probabilities: one observation flips a voxel).
 
-  python scripts/stress256.py --make-nref 6      # dev box: CPU oracle -> tests/golden/stress_nref.json
+  python tests/golden/make_stress_nref.py 6      # dev box: CPU oracle -> tests/golden/stress_nref.json
   python scripts/stress256.py --frames 6         # B200: FAST mode, events resident in HBM; prints one JSON line
 """
 import argparse
@@ -36,23 +36,7 @@ def frames(n, G=256):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=6)
-    ap.add_argument("--make-nref", type=int, default=0)
     a = ap.parse_args()
-    if a.make_nref:
-        from oracle import pyoracle
-        m = pyoracle.OracleMap(ORIGIN, RES, SIZE)
-        m.SetParameters(*scenes.PARAMS_TOGGLE)
-        allv = scenes.all_voxels(m.grid_size)
-        m.SetOccupancyBatchVox(allv, np.zeros(len(allv), np.uint8)); m.UpdateOccupancy(True); m.UpdateESDF()
-        rows = []
-        for f, (vox, occ) in enumerate(frames(a.make_nref)):
-            m.SetOccupancyBatchVox(vox, occ)
-            t0 = time.perf_counter(); m.UpdateOccupancy(True); m.UpdateESDF(); dt = time.perf_counter() - t0
-            s = m.stats()
-            rows.append(dict(frame=f, expansions=s["expansions"], inserts=s["inserts"], deletes=s["deletes"], cpu_update_s=round(dt, 3)))
-            print(rows[-1], flush=True)
-        json.dump(dict(oracle=m.kind, frames=rows), open(NREF, "w"), indent=1)
-        return
     import torch
     import fiesta_b200
     nref = json.load(open(NREF))["frames"] if os.path.exists(NREF) else []
