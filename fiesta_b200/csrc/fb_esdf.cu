@@ -25,6 +25,7 @@
 #include <cooperative_groups.h>
 #include <stdio.h>
 #include "fb_common.cuh"
+#include "fb_exit_test.h"
 
 namespace cg = cooperative_groups;
 
@@ -164,11 +165,7 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
   }
   // dirs_ (parameters.h:55-68) grouped by z-row so that the queue bits of all 24 neighbours come out of 13 mask words:
   // same row dz = -2,-1,+1,+2 | rows x-1, x+1, y-1, y+1 with dz = -1,0,+1 | the four xy diagonals | x-2, x+2, y-2, y+2
-  constexpr int kd[24][3] = {{0, 0, -2}, {0, 0, -1}, {0, 0, 1}, {0, 0, 2},
-                             {-1, 0, -1}, {-1, 0, 0}, {-1, 0, 1}, {1, 0, -1}, {1, 0, 0}, {1, 0, 1},
-                             {0, -1, -1}, {0, -1, 0}, {0, -1, 1}, {0, 1, -1}, {0, 1, 0}, {0, 1, 1},
-                             {-1, -1, 0}, {-1, 1, 0}, {1, -1, 0}, {1, 1, 0},
-                             {-2, 0, 0}, {2, 0, 0}, {0, -2, 0}, {0, 2, 0}};
+  constexpr int kd[24][3] = FBX_KD_INIT;
 #pragma unroll
   for (int k = 0; k < 24; ++k)
     if (tid == k) s_koff[k] = kd[k][0] * (FB_BOX * FB_BOXZ) + kd[k][1] * FB_BOXZ + kd[k][2];
@@ -434,13 +431,7 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
       if (nchanged) {
         // (X1) one thread per z-row of the box lists the halo voxels that have a changed record among their 24 neighbours
         if (tid < FB_BOX * FB_BOX) {
-          const int rx = tid / FB_BOX, ry = tid % FB_BOX, p = (rx + 2) * 16 + (ry + 2);
-          const uint32_t m0 = cmp[p];
-          const uint32_t f4 = cmp[p - 16] | cmp[p + 16] | cmp[p - 1] | cmp[p + 1];
-          uint32_t act = (m0 << 1) | (m0 >> 1) | (m0 << 2) | (m0 >> 2) | f4 | (f4 << 1) | (f4 >> 1) |
-                         cmp[p - 17] | cmp[p - 15] | cmp[p + 15] | cmp[p + 17] | cmp[p - 32] | cmp[p + 32] | cmp[p - 2] | cmp[p + 2];
-          const bool inner = rx >= FB_HALO && rx < FB_HALO + FB_TILE && ry >= FB_HALO && ry < FB_HALO + FB_TILE;
-          act &= inner ? (0x3ffcu & ~(0xffu << FB_ZPAD)) : 0x3ffcu;          // halo voxels within reach: box z 2..13
+          uint32_t act = fbx_row_candidates(cmp, tid / FB_BOX, tid % FB_BOX);
           if (act) {
             const unsigned cnt = (unsigned)__popc(act);
             unsigned pos = atomicAdd(&s_cnt[0], cnt);
@@ -464,39 +455,12 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
             const int e = e0 + lane / WF_GROUP;
             if (e >= n) continue;
             const int v = listV[e];
-            const int row = v >> 4, zb = v & 15, rx = row / FB_BOX, ry = row % FB_BOX, p = (rx + 2) * 16 + (ry + 2);
-            const int sidx = row * FB_BOXZ + zb;
-            const uint32_t cy = V[sidx] & FB_CODE_MASK;
+            const int row = v >> 4, zb = v & 15, rx = row / FB_BOX, ry = row % FB_BOX;
+            const uint32_t cy = V[row * FB_BOXZ + zb] & FB_CODE_MASK;
             const int x = x0 - FB_HALO + rx, y = y0 - FB_HALO + ry, z = z0 - FB_ZPAD + zb;
             if (cy == FB_UNKNOWN || !fb_in_range(g, x, y, z)) continue;      // barrier / outside the box (outside the grid: zero fill)
-            const uint32_t m0 = cmp[p];
-            uint32_t F = ((m0 >> (zb - 2)) & 3u) | (((m0 >> (zb + 1)) & 3u) << 2) |
-                         (((cmp[p - 16] >> (zb - 1)) & 7u) << 4) | (((cmp[p + 16] >> (zb - 1)) & 7u) << 7) |
-                         (((cmp[p - 1] >> (zb - 1)) & 7u) << 10) | (((cmp[p + 1] >> (zb - 1)) & 7u) << 13) |
-                         (((cmp[p - 17] >> zb) & 1u) << 16) | (((cmp[p - 15] >> zb) & 1u) << 17) |
-                         (((cmp[p + 15] >> zb) & 1u) << 18) | (((cmp[p + 17] >> zb) & 1u) << 19) |
-                         (((cmp[p - 32] >> zb) & 1u) << 20) | (((cmp[p + 32] >> zb) & 1u) << 21) |
-                         (((cmp[p - 2] >> zb) & 1u) << 22) | (((cmp[p + 2] >> zb) & 1u) << 23);
-            uint32_t m = F & (slice0 << sub);
-            if (!m) continue;
-            unsigned dy = 0xffffffffu;
-            if (cy >= 2u) { int px, py, pz; fb_unpack(cy, px, py, pz); px -= x; py -= y; pz -= z; dy = (unsigned)(px * px + py * py + pz * pz); }
-            bool improves = false;
-            while (m) {
-              const int k = __ffs(m) - 1;
-              m &= m - 1u;
-              const uint32_t c = V[sidx + s_koff[k]] & FB_CODE_MASK;       // a changed record of this tile (interior: in bounds)
-              if (c >= 2u && c != cy) {
-                int px, py, pz; fb_unpack(c, px, py, pz); px -= x; py -= y; pz -= z;
-                const unsigned d = (unsigned)(px * px + py * py + pz * pz);
-                improves = improves || d < dy || (d == dy && c < cy);
-              }
-            }
-            if (improves) {
-              const int ox = rx < FB_HALO ? -1 : rx >= FB_HALO + FB_TILE ? 1 : 0, oy = ry < FB_HALO ? -1 : ry >= FB_HALO + FB_TILE ? 1 : 0;
-              const int oz = zb < FB_ZPAD ? -1 : zb >= FB_ZPAD + FB_TILE ? 1 : 0;
-              atomicOr(&s_need, 1u << ((ox + 1) * 9 + (oy + 1) * 3 + (oz + 1)));
-            }
+            const uint32_t m = fbx_changed_neighbours(cmp, rx, ry, zb) & (slice0 << sub);
+            if (m && fbx_improves(V, s_koff, rx, ry, zb, x, y, z, cy, m)) atomicOr(&s_need, 1u << fbx_dir_bit(rx, ry, zb));
           }
         }
         __syncthreads();
