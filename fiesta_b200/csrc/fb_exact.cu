@@ -6,19 +6,8 @@
 // that order with data-parallel kernels (the CPU model of exactly this formulation is oracle/exact_model.c, which matches
 // the sequential reference voxel for voxel):
 //
-//  * Every FIFO generation is one list E of (voxel) entries in queue order.  Element i at direction k acts at the
-//    timestamp ts = 32*i + k (its pull acts at 32*i + 24).
-//  * A voxel's state "as seen at time T" is a pure function of the snapshot at generation start and of the behaviour
-//    (dead / pulled code / pushes code) of the <= 25 elements that can write it: the lexicographic minimum (distance,
-//    timestamp) over their offers with timestamp < T that beat the snapshot -- exactly what a sequence of strict `>` tests
-//    in timestamp order leaves behind (x_state()).
-//  * An element's behaviour depends only on states at its own pop time (k_x_eval); it is kept, together with the entry's
-//    queue position, in one packed per-voxel word so that a reader learns everything about a potential writer with one load.  Starting from "everybody pushes its
-//    snapshot code", the behaviours are re-evaluated until none changes; element i is right once all elements before it
-//    are, so the fixpoint is the sequential execution (2-3 rounds in practice).
-//  * The last accepted write to a voxel in a generation is the lexicographic minimum over ALL offers; those writes, in
-//    timestamp order, are the live entries of the next generation (k_x_commit + ordered compaction).  Non-final accepted
-//    writes only create entries the reference skips as stale (:345), so dropping them changes nothing.
+//  * E3, the FIFO relaxation loop, is one persistent kernel (fb_xrelax.cu): every FIFO generation is one ordered list of
+//    entries whose behaviours are resolved by a fixpoint over timestamped offers; see the header of that file.
 //  * The doubly linked dependant lists are replaced by a per-voxel link time LS (time of the last relink; every accepted
 //    write relinks at the list front, :24-42): dependants of deleted obstacles are found by a dense scan and ordered by
 //    (position of the obstacle in delete_queue_, link time descending) = the order of the reference's list walk; their
@@ -35,11 +24,9 @@
 #include "fb_exact.h"
 
 #define XNONE 0xffffffffu
-#define X_DEAD 0ull
-#define X_PULL 1ull
-#define X_PUSH 2ull
+#define XMB_NONE 0xffffffffffffffffull
 
-__constant__ int x_dirs[24][3] = {
+static __constant__ int x_dirs[24][3] = {
     {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
     {-1, -1, 0}, {1, 1, 0}, {0, -1, -1}, {0, 1, 1}, {-1, 0, -1}, {1, 0, 1},
     {-1, 1, 0}, {1, -1, 0}, {0, -1, 1}, {0, 1, -1}, {1, 0, -1}, {-1, 0, 1},
@@ -53,113 +40,6 @@ __device__ __forceinline__ unsigned x_d2(int x, int y, int z, uint32_t c) {
   return (unsigned)(ox * ox + oy * oy + oz * oz);
 }
 __device__ __forceinline__ unsigned x_dist_of(int x, int y, int z, uint32_t c) { return c < 2u ? 0xffffffffu : x_d2(x, y, z, c); }
-
-struct XState { unsigned d; uint32_t c; unsigned ts; };
-
-// Per-voxel packed word of the current generation: {queue position:27 | kind:2 | code:31}, all ones = no live entry here.
-// One 8-byte load tells a reader everything about a potential writer.
-#define XMB_NONE 0xffffffffffffffffull
-__device__ __forceinline__ unsigned long long x_mb(unsigned i, unsigned long long kind, uint32_t code) {
-  return ((unsigned long long)i << 33) | (kind << 31) | (unsigned long long)(code & FB_CODE_MASK);
-}
-__device__ __forceinline__ unsigned x_mb_idx(unsigned long long w) { return (unsigned)(w >> 33); }
-__device__ __forceinline__ unsigned long long x_mb_kind(unsigned long long w) { return (w >> 31) & 3ull; }
-__device__ __forceinline__ uint32_t x_mb_code(unsigned long long w) { return (uint32_t)(w & FB_CODE_MASK); }
-
-// State of voxel (x,y,z) as seen at time T (exclusive) given the behaviours of this generation's elements.
-__device__ __forceinline__ XState x_state(const FbGeom &g, const uint32_t *cobs, const unsigned long long *MB, int x, int y, int z, unsigned T) {
-  XState s;
-  const long long v = fb_ii(g, x, y, z);
-  s.c = cobs[v] & FB_CODE_MASK; s.d = x_dist_of(x, y, z, s.c); s.ts = XNONE;
-  const unsigned d0 = s.d;
-  if (s.c == FB_UNKNOWN) return s;                             // never observed: distance_ = -10000 is never > tmp (:382)
-  if (!fb_in_range(g, x, y, z)) return s;                     // pushes only go to voxels inside the update box (:378)
-#pragma unroll 8
-  for (int k = 0; k < 24; ++k) {
-    const int qx = x - x_dirs[k][0], qy = y - x_dirs[k][1], qz = z - x_dirs[k][2];
-    if (!fb_in_grid(g, qx, qy, qz)) continue;
-    const unsigned long long w = MB[fb_ii(g, qx, qy, qz)];
-    if (w == XMB_NONE || x_mb_kind(w) != X_PUSH) continue;
-    const unsigned ts = x_mb_idx(w) * 32u + (unsigned)k;
-    if (ts >= T) continue;
-    const uint32_t c = x_mb_code(w);
-    const unsigned d = x_d2(x, y, z, c);
-    if (d < d0 && (d < s.d || (d == s.d && ts < s.ts))) { s.d = d; s.c = c; s.ts = ts; }
-  }
-  const unsigned long long w = MB[v];
-  if (w != XMB_NONE && x_mb_kind(w) == X_PULL) {
-    const unsigned ts = x_mb_idx(w) * 32u + 24u;
-    if (ts < T) {
-      const uint32_t c = x_mb_code(w);
-      const unsigned d = x_d2(x, y, z, c);
-      if (d < d0 && (d < s.d || (d == s.d && ts < s.ts))) { s.d = d; s.c = c; s.ts = ts; }
-    }
-  }
-  return s;
-}
-
-
-// ---- per-voxel offer summaries ------------------------------------------------------------------------------------
-// Every voxel that some element of the generation can write (its 24 neighbours and itself) is a TARGET.  Once per round a
-// target's <= 25 offers are gathered into a summary {first = earliest timestamp of an offer that beats the snapshot,
-// best = lexicographic minimum (distance, timestamp) over all offers}.  A reader at time T then gets the snapshot if
-// T <= first, `best` if T > best.ts, and has to gather the offers itself only in between (about 1 % of the queries in the
-// CPU model, oracle/exact_model.c); non-targets have no writer and read as the snapshot.
-__device__ __forceinline__ uint4 x_summarize(const FbGeom &g, const uint32_t *cobs, const unsigned long long *MB, int x, int y, int z) {
-  const XState f = x_state(g, cobs, MB, x, y, z, XNONE);
-  unsigned first = XNONE;
-  const long long v = fb_ii(g, x, y, z);
-  const uint32_t c0 = cobs[v] & FB_CODE_MASK;
-  if (c0 != FB_UNKNOWN && fb_in_range(g, x, y, z)) {
-    const unsigned d0 = x_dist_of(x, y, z, c0);
-#pragma unroll 8
-    for (int k = 0; k < 24; ++k) {
-      const int qx = x - x_dirs[k][0], qy = y - x_dirs[k][1], qz = z - x_dirs[k][2];
-      if (!fb_in_grid(g, qx, qy, qz)) continue;
-      const unsigned long long w = MB[fb_ii(g, qx, qy, qz)];
-      if (w == XMB_NONE || x_mb_kind(w) != X_PUSH) continue;
-      const unsigned ts = x_mb_idx(w) * 32u + (unsigned)k;
-      if (ts < first && x_d2(x, y, z, x_mb_code(w)) < d0) first = ts;
-    }
-    const unsigned long long w = MB[v];
-    if (w != XMB_NONE && x_mb_kind(w) == X_PULL) {
-      const unsigned ts = x_mb_idx(w) * 32u + 24u;
-      if (ts < first && x_d2(x, y, z, x_mb_code(w)) < d0) first = ts;
-    }
-  }
-  return make_uint4(first, f.d, f.ts, f.c);
-}
-__device__ __forceinline__ XState x_state_sum(const FbGeom &g, const uint32_t *cobs, const unsigned long long *MB, const uint4 *SUM,
-                                              const uint32_t *SUMg, unsigned gen, int x, int y, int z, unsigned T) {
-  const long long v = fb_ii(g, x, y, z);
-  XState s;
-  bool snapshot = SUMg[v] != gen;
-  uint4 u = make_uint4(0, 0, 0, 0);
-  if (!snapshot) { u = SUM[v]; snapshot = u.x == XNONE || T <= u.x; }
-  if (snapshot) { s.c = cobs[v] & FB_CODE_MASK; s.d = x_dist_of(x, y, z, s.c); s.ts = XNONE; return s; }
-  if (T > u.z) { s.d = u.y; s.ts = u.z; s.c = u.w; return s; }
-  return x_state(g, cobs, MB, x, y, z, T);                    // first < T <= best.ts: gather
-}
-// Targets of the generation (deduplicated through SUMg).
-__global__ void k_x_targets(FbGeom g, const uint32_t *E, unsigned n, uint32_t *SUMg, unsigned gen, uint32_t *targets, unsigned *ntargets) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int x, y, z; x_coords(g, E[i], x, y, z);
-  for (int k = 0; k < 25; ++k) {
-    const int nx = k < 24 ? x + x_dirs[k][0] : x, ny = k < 24 ? y + x_dirs[k][1] : y, nz = k < 24 ? z + x_dirs[k][2] : z;
-    if (!fb_in_range(g, nx, ny, nz) || !fb_in_grid(g, nx, ny, nz)) continue;
-    const long long v = fb_ii(g, nx, ny, nz);
-    if (SUMg[v] != gen && atomicExch(&SUMg[v], gen) != gen) targets[atomicAdd(ntargets, 1u)] = (uint32_t)v;
-  }
-}
-__global__ void k_x_sum(FbGeom g, const uint32_t *targets, unsigned nt, const uint32_t *cobs, const unsigned long long *MB, uint4 *SUM,
-                        const uint32_t *tdirty, unsigned stamp, int first_round) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nt) return;
-  int x, y, z; x_coords(g, targets[i], x, y, z);
-  if (!first_round && tdirty[((x >> 3) * g.ty + (y >> 3)) * g.tz + (z >> 3)] != stamp) return;
-  SUM[targets[i]] = x_summarize(g, cobs, MB, x, y, z);
-}
 
 // ------------------------------------------------------------------ occupancy (ordered)
 __global__ void k_x_gather_keys(const uint32_t *vox, unsigned n, const unsigned long long *tkey, unsigned long long *keys) {
@@ -251,176 +131,6 @@ __global__ void k_x_set_ord(const uint32_t *deps, unsigned n, uint32_t *ord, uin
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { ord[deps[i]] = i; nc[i] = FB_INF; }
 }
-// One round of the re-seeding fixpoint: dependant i takes the closest obstacle of the FIRST neighbour in dirs_ order that
-// has a valid one (:308-321); dependants processed earlier expose their new value, later ones their (deleted) old one.
-__global__ void k_x_reseed(FbGeom g, const uint32_t *deps, unsigned n, const uint32_t *cobs, const uint32_t *ord, const uint32_t *occbits,
-                           const uint32_t *nc_in, uint32_t *nc_out, unsigned *changed) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int x, y, z; x_coords(g, deps[i], x, y, z);
-  uint32_t res = FB_INF;
-  for (int k = 0; k < 24; ++k) {
-    const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
-    if (!fb_in_range(g, nx, ny, nz) || !fb_in_grid(g, nx, ny, nz)) continue;
-    const long long nv = fb_ii(g, nx, ny, nz);
-    const unsigned o = ord[nv];
-    uint32_t c;
-    if (o != XNONE) { if (o < i) c = nc_in[o]; else continue; }
-    else c = cobs[nv] & FB_CODE_MASK;
-    if (c >= 2u) {
-      int ox, oy, oz; fb_unpack(c, ox, oy, oz);
-      const long long oi = fb_ii(g, ox, oy, oz);
-      if ((occbits[oi >> 5] >> (oi & 31)) & 1u) { res = c; break; }             // Exist(closest obstacle) (:312), then `break` (:319)
-    }
-  }
-  nc_out[i] = res;
-  if (res != nc_in[i]) *changed = 1u;
-}
-__global__ void k_x_apply_reseed(const uint32_t *deps, unsigned n, const uint32_t *nc, uint32_t *cobs, unsigned long long *LS,
-                                 unsigned long long t0, uint8_t *flags) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  cobs[deps[i]] = nc[i];
-  LS[deps[i]] = t0 + i;                                        // InsertIntoList(new_obs_idx, obs_idx) (:333)
-  flags[i] = nc[i] >= 2u;                                      // `if (distance < infinity_) update_queue_.push` (:329-331)
-}
-// ------------------------------------------------------------------ E3: relax, one FIFO generation at a time
-// Initial guess of the behaviour fixpoint: every entry is live and pushes its snapshot code.
-__global__ void k_x_init_beh(const uint32_t *E, unsigned n, const uint32_t *cobs, unsigned long long *MB) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) MB[E[i]] = x_mb(i, X_PUSH, cobs[E[i]]);
-}
-// One round of the behaviour fixpoint.  B is updated IN PLACE (elements evaluated later in the same round already see the
-// new behaviour of earlier ones); an element is re-evaluated only in the first round of a generation or when an element
-// within reach (<= 4 voxels: its own 8^3 tile or one of the 26 around it) changed its behaviour in the previous round.
-// The loop ends with a round in which nothing changed, which reads a stable B: that state is the sequential execution.
-__global__ void k_x_eval(FbGeom g, const uint32_t *E, unsigned n, const uint32_t *cobs, unsigned long long *MB, const uint4 *SUM,
-                         const uint32_t *SUMg, unsigned gen, uint32_t *tdirty, unsigned stamp, int first_round, unsigned *changed) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t p = E[i];
-  int x, y, z; x_coords(g, p, x, y, z);
-  const int tx = x >> 3, ty = y >> 3, tz = z >> 3;
-  if (!first_round && tdirty[(tx * g.ty + ty) * g.tz + tz] != stamp) return;
-  const unsigned T0 = i * 32u;
-  const XState s = x_state_sum(g, cobs, MB, SUM, SUMg, gen, x, y, z, T0);
-  const uint32_t c0 = cobs[p] & FB_CODE_MASK;
-  unsigned long long nb;
-  if (s.d != x_dist_of(x, y, z, c0)) nb = x_mb(i, X_DEAD, 0);  // `xx.distance_ != distance_buffer_[idx]`: stale (:345)
-  else {
-    unsigned curd = s.d; uint32_t curc = s.c; bool ch = false;
-    for (int k = 0; k < 24; ++k) {                             // pull phase (:349-367)
-      const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
-      if (!fb_in_range(g, nx, ny, nz) || !fb_in_grid(g, nx, ny, nz)) continue;
-      const XState sn = x_state_sum(g, cobs, MB, SUM, SUMg, gen, nx, ny, nz, T0);
-      if (sn.c < 2u) continue;
-      const unsigned t = x_d2(x, y, z, sn.c);
-      if (curd > t) { curd = t; curc = sn.c; ch = true; }
-    }
-    nb = ch ? x_mb(i, X_PULL, curc) : x_mb(i, X_PUSH, s.c);
-  }
-  if (nb != MB[p]) {
-    MB[p] = nb;
-    *changed = 1u;
-    for (int a = max(tx - 1, 0); a <= min(tx + 1, g.tx - 1); ++a)
-      for (int b = max(ty - 1, 0); b <= min(ty + 1, g.ty - 1); ++b)
-        for (int c = max(tz - 1, 0); c <= min(tz + 1, g.tz - 1); ++c) tdirty[(a * g.ty + b) * g.tz + c] = stamp + 1u;
-  }
-}
-// The same evaluation with one WARP per element, for the rounds after the first: only the few elements in dirty tiles do
-// any work there, so the round's duration is the latency of a single evaluation -- 25 state queries run on 25 lanes
-// instead of one after the other.  The sequential pull loop "for k: if (dist > tmp) take" (:349-367) is the lexicographic
-// minimum (tmp, k) over the neighbours that beat the own distance (warp reduction).
-// Elements whose tile is dirty for this round -> work list (so that the evaluation kernel is not launched over millions
-// of idle threads).
-__global__ void k_x_collect(FbGeom g, const uint32_t *E, unsigned n, const uint32_t *tdirty, unsigned stamp, uint32_t *work, unsigned *nwork) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool on = false;
-  if (i < n) { int x, y, z; x_coords(g, E[i], x, y, z); on = tdirty[((x >> 3) * g.ty + (y >> 3)) * g.tz + (z >> 3)] == stamp; }
-  const unsigned slot = fb_warp_append(nwork, on);
-  if (on) work[slot] = i;
-}
-__global__ void k_x_eval_warp(FbGeom g, const uint32_t *E, const uint32_t *work, const unsigned *nwork, const uint32_t *cobs, unsigned long long *MB,
-                              const uint4 *SUM, const uint32_t *SUMg, unsigned gen, uint32_t *tdirty, unsigned stamp, unsigned *changed) {
-  const unsigned lane = threadIdx.x & 31u, nw = *nwork;
-  for (unsigned wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < nw; wi += (gridDim.x * blockDim.x) >> 5) {
-  const unsigned i = work[wi];
-  const uint32_t p = E[i];
-  int x, y, z; x_coords(g, p, x, y, z);
-  const int tx = x >> 3, ty = y >> 3, tz = z >> 3;
-  const unsigned T0 = i * 32u;
-  int qx = x, qy = y, qz = z;
-  bool valid = lane == 24;
-  if (lane < 24) { qx += x_dirs[lane][0]; qy += x_dirs[lane][1]; qz += x_dirs[lane][2]; valid = fb_in_range(g, qx, qy, qz) && fb_in_grid(g, qx, qy, qz); }
-  XState st; st.d = 0xffffffffu; st.c = 0; st.ts = XNONE;
-  if (valid) st = x_state_sum(g, cobs, MB, SUM, SUMg, gen, qx, qy, qz, T0);   // lanes 0..23: neighbour k at pop time; lane 24: the element itself
-  const unsigned sd = __shfl_sync(0xffffffffu, st.d, 24);
-  const uint32_t sc = __shfl_sync(0xffffffffu, st.c, 24);
-  const uint32_t c0 = cobs[p] & FB_CODE_MASK;
-  unsigned long long nb;
-  if (sd != x_dist_of(x, y, z, c0)) nb = x_mb(i, X_DEAD, 0);
-  else {
-    unsigned long long key = ~0ull;
-    if (lane < 24 && valid && st.c >= 2u) {
-      const unsigned t = x_d2(x, y, z, st.c);
-      if (t < sd) key = ((unsigned long long)t << 8) | lane;
-    }
-    unsigned long long best = key;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o); best = other < best ? other : best; }
-    if (best == ~0ull) nb = x_mb(i, X_PUSH, sc);
-    else nb = x_mb(i, X_PULL, __shfl_sync(0xffffffffu, st.c, (int)(best & 0xffu)));
-  }
-  if (lane == 0 && nb != MB[p]) {
-    MB[p] = nb;
-    *changed = 1u;
-    for (int a = max(tx - 1, 0); a <= min(tx + 1, g.tx - 1); ++a)
-      for (int b = max(ty - 1, 0); b <= min(ty + 1, g.ty - 1); ++b)
-        for (int c = max(tz - 1, 0); c <= min(tz + 1, g.tz - 1); ++c) tdirty[(a * g.ty + b) * g.tz + c] = stamp + 1u;
-  }
-  }
-}
-// Final writes of the generation -> slots (timestamp order) of the next generation's queue.
-__global__ void k_x_commit(FbGeom g, const uint32_t *E, unsigned n, const unsigned long long *MB, const uint4 *SUM, const uint32_t *SUMg, unsigned gen,
-                           uint32_t *slotv, uint32_t *slotc, uint8_t *slotf, unsigned long long *expansions) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long b = XMB_NONE;
-  if (i < n) b = MB[E[i]];
-  const bool live = i < n && x_mb_kind(b) != X_DEAD;
-  const unsigned nlive = __popc(__ballot_sync(0xffffffffu, live));
-  if ((threadIdx.x & 31) == 0 && nlive) atomicAdd(expansions, (unsigned long long)nlive);   // `times++` (:347)
-  if (!live) return;
-  int x, y, z; x_coords(g, E[i], x, y, z);
-  // The last accepted write to a voxel is its summary's `best`; the element/direction that made it owns the slot.
-  if (x_mb_kind(b) == X_PUSH) {
-    for (int k = 0; k < 24; ++k) {                             // push phase (:375-391)
-      const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
-      if (!fb_in_range(g, nx, ny, nz) || !fb_in_grid(g, nx, ny, nz)) continue;
-      const long long v = fb_ii(g, nx, ny, nz);
-      const unsigned ts = i * 32u + (unsigned)k;
-      if (SUMg[v] != gen) continue;
-      const uint4 u = SUM[v];
-      if (u.z == ts) { slotv[ts] = (uint32_t)v; slotc[ts] = u.w; slotf[ts] = 1; }
-    }
-  } else {
-    const unsigned ts = i * 32u + 24u;
-    const uint4 u = SUM[E[i]];
-    if (SUMg[E[i]] == gen && u.z == ts) { slotv[ts] = E[i]; slotc[ts] = u.w; slotf[ts] = 1; }
-  }
-}
-__global__ void k_x_clear_M(const uint32_t *E, unsigned n, unsigned long long *MB) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) MB[E[i]] = XMB_NONE;
-}
-__global__ void k_x_apply(const uint32_t *sel, unsigned n, const uint32_t *slotv, const uint32_t *slotc, uint32_t *cobs,
-                          unsigned long long *LS, unsigned long long t0, uint32_t *Enext) {
-  const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  const uint32_t s = sel[r], v = slotv[s];
-  cobs[v] = slotc[s];
-  LS[v] = t0 + s;                                              // every accepted write relinks the voxel at its list's front
-  Enext[r] = v;
-}
 __global__ void k_x_fill32(uint32_t *a, size_t n, uint32_t val) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] = val;
 }
@@ -469,35 +179,40 @@ static cudaError_t x_sort_pairs(FbExact *X, const unsigned long long *kin, unsig
   XCK(cub::DeviceRadixSort::SortPairs(X->cub_tmp, bytes, kin, kout, vin, vout, (int)n, 0, 64, s));
   return cudaSuccess;
 }
-static cudaError_t x_flag(FbExact *X, cudaStream_t s, unsigned *out) {   // read-and-clear the device "changed" flag
-  XCK(cudaMemcpyAsync(X->h_count, X->d_flag, 4, cudaMemcpyDeviceToHost, s));
-  XCK(cudaMemsetAsync(X->d_flag, 0, 4, s));
-  XCK(cudaStreamSynchronize(s));
-  *out = *X->h_count;
-  return cudaSuccess;
-}
-
-cudaError_t fb_exact_init(FbExact *X, const FbGeom &g, cudaStream_t s) {
+cudaError_t fb_exact_init(FbExact *X, const FbGeom &g, int device, cudaStream_t s) {
   memset(X, 0, sizeof(*X));
   const size_t P = (size_t)g.ptotal;
+  XCK(fb_xrelax_init());
+  X->relax_blocks = fb_xrelax_blocks(device);
+  if (X->relax_blocks <= 0 || X->relax_blocks > FB_X_MAX_BLOCKS) { snprintf(X->err, sizeof(X->err), "k_x_relax does not fit on this device"); return cudaErrorInvalidConfiguration; }
   XCK(cudaMalloc((void **)&X->MB, P * 8)); XCK(cudaMalloc((void **)&X->LS, P * 8)); XCK(cudaMalloc((void **)&X->tkey, P * 8));
   XCK(cudaMalloc((void **)&X->touched, P * 4));
   XCK(cudaMalloc((void **)&X->SUM, P * 16)); XCK(cudaMalloc((void **)&X->SUMg, P * 4)); XCK(cudaMemsetAsync(X->SUMg, 0, P * 4, s));
-  XCK(cudaMalloc((void **)&X->tdirty, (size_t)g.ntiles * 4)); XCK(cudaMemsetAsync(X->tdirty, 0, (size_t)g.ntiles * 4, s));
+  XCK(cudaMalloc((void **)&X->T, P * 4)); XCK(cudaMalloc((void **)&X->emask, P * 4));
+  XCK(cudaMalloc((void **)&X->wstamp, P * 4)); XCK(cudaMemsetAsync(X->wstamp, 0, P * 4, s));
+  for (int k = 0; k < 3; ++k) { XCK(cudaMalloc((void **)&X->W[k], P * 4)); XCK(cudaMalloc((void **)&X->F[k], P * 4)); }
+  for (int k = 0; k < 2; ++k) { XCK(cudaMalloc((void **)&X->E[k], P * 4)); X->cap_E[k] = P; }
+  X->small_max = FB_X_SMALL_DEFAULT;
+  if (const char *e = getenv("FIESTA_X_SMALL")) { long v = atol(e); if (v >= 0 && v <= 65536) X->small_max = (unsigned)v; }
+  XCK(cudaMalloc((void **)&X->slotc, ((size_t)X->small_max + 1) * 32 * 4));
+  XCK(cudaMalloc((void **)&X->d_ctl, sizeof(FbXCtl))); XCK(cudaMemsetAsync(X->d_ctl, 0, sizeof(FbXCtl), s));
+  XCK(cudaMallocHost((void **)&X->h_ctl, sizeof(FbXCtl)));
   XCK(cudaMalloc((void **)&X->d_count, 16)); XCK(cudaMalloc((void **)&X->d_flag, 16));
   XCK(cudaMallocHost((void **)&X->h_count, 16));
   XCK(cudaMemsetAsync(X->d_count, 0, 16, s)); XCK(cudaMemsetAsync(X->d_flag, 0, 16, s));
   k_x_fill64<<<148 * 8, 256, 0, s>>>(X->MB, P, XMB_NONE);
   k_x_fill64<<<148 * 8, 256, 0, s>>>(X->tkey, P, ~0ull);
   XCK(cudaMemsetAsync(X->LS, 0, P * 8, s));
-  X->tclock = 1; X->key_base = 0; X->eval_clock = 1; X->gen_id = 0;
+  X->tclock = 1; X->key_base = 0; X->gen_id = 0; X->wclock = 0;
   return cudaGetLastError();
 }
 void fb_exact_free(FbExact *X) {
-  void *p[] = {X->MB, X->LS, X->tkey, X->touched, X->tdirty, X->SUM, X->SUMg, X->targets, X->work, X->d_count, X->d_flag, X->E[0], X->E[1], X->slotv, X->slotc, X->slotf, X->sel,
+  void *p[] = {X->MB, X->LS, X->tkey, X->touched, X->SUM, X->SUMg, X->T, X->emask, X->wstamp, X->W[0], X->W[1], X->W[2], X->F[0], X->F[1], X->F[2], X->slotc,
+               X->d_ctl, X->d_dbg, X->d_count, X->d_flag, X->E[0], X->E[1], X->sel,
                X->k1, X->k2, X->k1b, X->k2b, X->dv, X->idx[0], X->idx[1], X->deps, X->nc[0], X->nc[1], X->flags, X->flags2, X->cub_tmp};
   for (void *q : p) if (q) cudaFree(q);
   if (X->h_count) cudaFreeHost(X->h_count);
+  if (X->h_ctl) cudaFreeHost(X->h_ctl);
   memset(X, 0, sizeof(*X));
 }
 
@@ -545,9 +260,13 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
   const size_t P = (size_t)g.ptotal;
   memset(st, 0, sizeof(*st));
   if ((e = x_ensure(X, &X->flags, &X->cap_flags, (size_t)(n_ins > n_del ? n_ins : n_del) + 16))) return e;
-  if ((e = x_ensure(X, &X->E[0], &X->cap_E[0], (size_t)n_ins + 16))) return e;
+  static const bool xdbg = getenv("FIESTA_DEBUG_X") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t_begin = now();
   // ---- E1: insert seeds in insert_queue_ order (:278-291)
-  unsigned nE = 0;
+  unsigned nE = 0, ndep_run = 0;
+  unsigned long long ls_deps = 0;
   if (n_ins) {
     k_x_flag_exist<<<nblk(n_ins), 256, 0, s>>>(ins, n_ins, occ, l_occ, X->flags, 1);
     if ((e = x_select(X, ins, X->flags, X->E[0], n_ins, &nE, s))) return e;
@@ -601,115 +320,43 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
         k_x_fill32<<<148 * 8, 256, 0, s>>>(scratch, P, XNONE);
         k_x_set_ord<<<nblk(ndep), 256, 0, s>>>(X->deps, ndep, scratch, X->nc[0]);
         *launches += 8;
-        int cur = 0;
-        for (int it = 0; it < 100000; ++it) {
-          k_x_reseed<<<nblk(ndep), 256, 0, s>>>(g, X->deps, ndep, cobs, scratch, occbits, X->nc[cur], X->nc[cur ^ 1], X->d_flag);
-          *launches += 1;
-          cur ^= 1;
-          unsigned ch = 0;
-          if ((e = x_flag(X, s, &ch))) return e;
-          st->reseed_rounds++;
-          if (!ch) break;
-        }
-        k_x_apply_reseed<<<nblk(ndep), 256, 0, s>>>(X->deps, ndep, X->nc[cur], cobs, X->LS, X->tclock, X->flags);
+        ndep_run = ndep; ls_deps = X->tclock;                // the fixpoint and the hand-over to E[0] run inside k_x_relax
         X->tclock += ndep;
-        if ((e = x_ensure(X, &X->E[1], &X->cap_E[1], (size_t)nE + ndep + 16))) return e;   // E[0] may be too small: rebuild in E[1]
-        if (nE) XCK(cudaMemcpyAsync(X->E[1], X->E[0], (size_t)nE * 4, cudaMemcpyDeviceToDevice, s));
-        unsigned nr = 0;
-        if ((e = x_select(X, X->deps, X->flags, X->E[1] + nE, ndep, &nr, s))) return e;
-        // keep the generation-0 list in E[0]
-        if ((e = x_ensure(X, &X->E[0], &X->cap_E[0], (size_t)nE + nr + 16))) return e;
-        XCK(cudaMemcpyAsync(X->E[0], X->E[1], (size_t)(nE + nr) * 4, cudaMemcpyDeviceToDevice, s));
-        nE += nr;
-        *launches += 3;
       }
     }
   }
-  // ---- E3: relax (:338-392)
-  static const bool xdbg = getenv("FIESTA_DEBUG_X") != nullptr;
-  auto now = [] { return std::chrono::steady_clock::now(); };
-  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-  double t_eval = 0, t_commit = 0, t_select = 0, t_apply = 0, t_k[5] = {0, 0, 0, 0, 0}; auto t_start = now();
-  auto lap = [&](int k, std::chrono::steady_clock::time_point &a) { if (xdbg) { cudaStreamSynchronize(s); auto b = now(); t_k[k] += ms(a, b); a = b; } };
-  int cur = 0;
-  XCK(cudaMemsetAsync(X->d_count + 2, 0, 8, s));               // expansions counter (u64 at d_count[2..3])
-  while (nE) {
-    st->generations++;
-    const size_t nslots = (size_t)nE * 32;
-    if (nE >= (1u << 27)) { snprintf(X->err, sizeof(X->err), "exact mode: generation with more than 2^27 entries"); return cudaErrorInvalidValue; }
-    if ((e = x_ensure(X, &X->slotv, &X->cap_slotv, nslots))) return e;
-    if ((e = x_ensure(X, &X->slotc, &X->cap_slotc, nslots))) return e;
-    if ((e = x_ensure(X, &X->slotf, &X->cap_slotf, nslots))) return e;
-    if ((e = x_ensure(X, &X->sel, &X->cap_sel, nslots))) return e;
-    auto t0 = now();
-    k_x_init_beh<<<nblk(nE), 256, 0, s>>>(X->E[cur], nE, cobs, X->MB);
-    // targets of this generation
-    ++X->gen_id;
-    if ((e = x_ensure(X, &X->targets, &X->cap_targets, (size_t)nE * 25))) return e;
-    if ((e = x_ensure(X, &X->work, &X->cap_work, (size_t)nE))) return e;
-    XCK(cudaMemsetAsync(X->d_count, 0, 4, s));
-    auto tl = now();
-    k_x_targets<<<nblk(nE), 256, 0, s>>>(g, X->E[cur], nE, X->SUMg, X->gen_id, X->targets, X->d_count);
-    XCK(cudaMemcpyAsync(X->h_count, X->d_count, 4, cudaMemcpyDeviceToHost, s));
+  // ---- E3: relax (:338-392): one persistent kernel runs every generation
+  st->generations = 0;
+  if (xdbg) { cudaStreamSynchronize(s); fprintf(stderr, "[x] seeds+deletes %.2f ms (reseed rounds %u, dependants %u)\n", ms(t_begin, now()), st->reseed_rounds, st->dependants); }
+  if (nE || ndep_run) {
+    if (xdbg && !X->d_dbg) XCK(cudaMalloc((void **)&X->d_dbg, FB_X_DBG_WORDS * 8));
+    if (xdbg) XCK(cudaMemsetAsync(X->d_dbg, 0, FB_X_DBG_WORDS * 8, s));
+    if (X->gen_id > 0xf0000000u) { XCK(cudaMemsetAsync(X->SUMg, 0, P * 4, s)); X->gen_id = 0; }       // stamp wrap-around
+    if (X->wclock > 0xf0000000u) { XCK(cudaMemsetAsync(X->wstamp, 0, P * 4, s)); X->wclock = 0; }
+    FbXCtl *h = X->h_ctl;
+    memset(h, 0, sizeof(*h));
+    h->gen_id = X->gen_id; h->wclock = X->wclock; h->tclock = X->tclock;
+    XCK(cudaMemcpyAsync(X->d_ctl, h, sizeof(FbXCtl), cudaMemcpyHostToDevice, s));
+    XCK(fb_xrelax_launch(X, g, cobs, nE, X->deps, ndep_run, scratch, X->nc[0], occbits, ls_deps, xdbg ? X->d_dbg : nullptr, s));
+    XCK(cudaMemcpyAsync(h, X->d_ctl, sizeof(FbXCtl), cudaMemcpyDeviceToHost, s));
     XCK(cudaStreamSynchronize(s));
-    const unsigned nT = *X->h_count;
-    *launches += 2;
-    lap(0, tl);
-    // Rounds are launched four at a time between host checks: a round after convergence finds no dirty tile and costs
-    // next to nothing, and a batch that changed nothing proves that the last state survived a full round.
-    for (int it = 0; it < 100000; it += 4) {
-      for (int q = 0; q < 4; ++q) {
-        ++X->eval_clock;
-        const int first = it + q == 0;
-        k_x_sum<<<nblk(nT), 256, 0, s>>>(g, X->targets, nT, cobs, X->MB, X->SUM, X->tdirty, X->eval_clock, first);
-        lap(1, tl);
-        if (first) { k_x_eval<<<nblk(nE, 128), 128, 0, s>>>(g, X->E[cur], nE, cobs, X->MB, X->SUM, X->SUMg, X->gen_id, X->tdirty, X->eval_clock, 1, X->d_flag); lap(2, tl); }
-        else {
-          XCK(cudaMemsetAsync(X->d_count + 1, 0, 4, s));
-          k_x_collect<<<nblk(nE), 256, 0, s>>>(g, X->E[cur], nE, X->tdirty, X->eval_clock, X->work, X->d_count + 1);
-          lap(3, tl);
-          k_x_eval_warp<<<148 * 4, 256, 0, s>>>(g, X->E[cur], X->work, X->d_count + 1, cobs, X->MB, X->SUM, X->SUMg, X->gen_id, X->tdirty, X->eval_clock, X->d_flag);
-          lap(4, tl);
-        }
-      }
-      *launches += 10;
-      unsigned ch = 0;
-      if ((e = x_flag(X, s, &ch))) return e;
-      st->eval_rounds += 4;
-      if (!ch) break;
+    *launches += 1;
+    if (h->err) { snprintf(X->err, sizeof(X->err), "exact mode: generation with more than 2^27 entries"); return cudaErrorInvalidValue; }
+    X->gen_id = h->gen_id; X->wclock = h->wclock; X->tclock = h->tclock;
+    st->generations = h->generations; st->reseed_rounds = h->reseed_rounds; st->eval_rounds = h->rounds; st->dense_rounds = h->dense_rounds;
+    st->voxels_changed = h->voxels_changed; st->expansions = h->expansions;
+    if (xdbg) {
+      static unsigned long long hd[FB_X_DBG_WORDS];
+      XCK(cudaMemcpy(hd, X->d_dbg, sizeof(hd), cudaMemcpyDeviceToHost));
+      static const char *cat[12] = {"S", "round1", "rounds", "dense", "commit", "apply", "s.round1", "s.rounds", "s.commit", "s.apply", "top", "empty-barrier(cycles)"};
+      fprintf(stderr, "[x] reseed rounds %u; phases (us, count):", st->reseed_rounds);
+      for (int c = 0; c < 12; ++c) fprintf(stderr, " %s %.0f/%llu", cat[c], hd[3 * 1024 + 2 * c] / 1965.0, hd[3 * 1024 + 2 * c + 1]);
+      fprintf(stderr, "\n");
+      for (int gq = 0; gq < 2; ++gq) { fprintf(stderr, "[x] gen %d work lists:", gq); for (int r = 0; r < 512 && hd[3 * 1024 + 32 + gq * 512 + r]; ++r) fprintf(stderr, " %llu", hd[3 * 1024 + 32 + gq * 512 + r]); fprintf(stderr, "\n"); }
+      fprintf(stderr, "[x] gens %u rounds %u dense %u deps %u nE0 %u |", st->generations, st->eval_rounds, st->dense_rounds, st->dependants, nE);
+      for (unsigned q = 0; q < st->generations && q < 1024; ++q) fprintf(stderr, " %llu/%llu/%.1fus", hd[3 * q], hd[3 * q + 1], hd[3 * q + 2] / 1965.0);
+      fprintf(stderr, "\n");
     }
-    auto t1 = now();
-    XCK(cudaMemsetAsync(X->slotf, 0, nslots, s));
-    k_x_commit<<<nblk(nE, 128), 128, 0, s>>>(g, X->E[cur], nE, X->MB, X->SUM, X->SUMg, X->gen_id, X->slotv, X->slotc, X->slotf, (unsigned long long *)(X->d_count + 2));
-    k_x_clear_M<<<nblk(nE), 256, 0, s>>>(X->E[cur], nE, X->MB);
-    if (xdbg) cudaStreamSynchronize(s);
-    auto t2 = now();
-    unsigned n2 = 0;
-    {
-      size_t bytes = 0;
-      cub::CountingInputIterator<uint32_t> it0(0);
-      XCK(cub::DeviceSelect::Flagged(nullptr, bytes, it0, X->slotf, X->sel, X->d_count, (int)nslots, s));
-      if ((e = x_tmp(X, bytes))) return e;
-      XCK(cub::DeviceSelect::Flagged(X->cub_tmp, bytes, it0, X->slotf, X->sel, X->d_count, (int)nslots, s));
-      XCK(cudaMemcpyAsync(X->h_count, X->d_count, 4, cudaMemcpyDeviceToHost, s));
-      XCK(cudaStreamSynchronize(s));
-      n2 = *X->h_count;
-    }
-    auto t3 = now();
-    if ((e = x_ensure(X, &X->E[cur ^ 1], &X->cap_E[cur ^ 1], (size_t)n2 + 16))) return e;
-    if (n2) k_x_apply<<<nblk(n2), 256, 0, s>>>(X->sel, n2, X->slotv, X->slotc, cobs, X->LS, X->tclock, X->E[cur ^ 1]);
-    *launches += 5;
-    if (xdbg) cudaStreamSynchronize(s);
-    auto t4 = now();
-    t_eval += ms(t0, t1); t_commit += ms(t1, t2); t_select += ms(t2, t3); t_apply += ms(t3, t4);
-    X->tclock += nslots + 1;
-    st->voxels_changed += n2;
-    cur ^= 1;
-    nE = n2;
   }
-  XCK(cudaMemcpyAsync(X->h_count, X->d_count + 2, 8, cudaMemcpyDeviceToHost, s));
-  XCK(cudaStreamSynchronize(s));
-  st->expansions = *(unsigned long long *)X->h_count;
-  if (xdbg) fprintf(stderr, "[x] gens %u rounds %u deps %u | relax %.1f ms: eval %.1f (targets %.1f sum %.1f eval1 %.1f collect %.1f evalw %.1f) commit %.1f select %.1f apply %.1f\n", st->generations, st->eval_rounds, st->dependants, ms(t_start, now()), t_eval, t_k[0], t_k[1], t_k[2], t_k[3], t_k[4], t_commit, t_select, t_apply);
   return cudaSuccess;
 }

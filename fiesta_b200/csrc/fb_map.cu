@@ -415,7 +415,7 @@ int fiesta_create(const fiesta_config *cfg, fiesta_map **out) {
   m->wf_blocks = fb_esdf_wavefront_blocks(m->device);
   m->rr_blocks = fb_ray_resolve_blocks(m->device);
   if (m->wf_blocks <= 0 || m->rr_blocks <= 0) { set_error("cooperative kernels do not fit on this device"); fiesta_destroy(m); return FIESTA_ERR_CUDA; }
-  if (m->mode == FIESTA_MODE_EXACT && fb_exact_init(&m->X, g, m->stream) != cudaSuccess) { set_error("exact mode init: %s", m->X.err); fiesta_destroy(m); return FIESTA_ERR_CUDA; }
+  if (m->mode == FIESTA_MODE_EXACT && fb_exact_init(&m->X, g, m->device, m->stream) != cudaSuccess) { set_error("exact mode init: %s", m->X.err); fiesta_destroy(m); return FIESTA_ERR_CUDA; }
   CKD(cudaStreamSynchronize(m->stream));
 #undef CKD
   *out = m;

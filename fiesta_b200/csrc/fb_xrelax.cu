@@ -1,0 +1,605 @@
+// fiesta_b200 -- ORDER-EXACT mode, E3: the FIFO relaxation loop of UpdateESDF (/root/reference/src/ESDFMap.cpp:338-392) as ONE
+// persistent kernel, k_x_relax: every FIFO generation, every round of its behaviour fixpoint and the ordered hand-over to
+// the next generation run on the device, separated by grid barriers; the host launches it once per UpdateESDF and reads
+// one control block back.  (CPU model of exactly this formulation: oracle/exact_model.c.)
+//
+//  * A FIFO generation is one list E of voxels in queue order.  Element i, direction k acts at the timestamp 32*i + k
+//    (its pull at 32*i + 24).  MB[v] is the packed word {queue position, behaviour, code} of the live entry at voxel v.
+//  * state(v, T): what voxel v holds at time T = the snapshot, or the lexicographic minimum (distance, timestamp) over the
+//    offers with timestamp < T of the <= 25 elements that can write v which beat the snapshot -- exactly what a sequence
+//    of strict `>` tests in timestamp order leaves behind (x_gather).  BIG generations cache, per target voxel, a summary
+//    {first improving timestamp, best timestamp, best code, snapshot code}; a query gathers only if first < T <= best.
+//  * An element's behaviour (stale / pulled code / pushes code, :345-373) depends only on states at its own pop time.
+//    Round 1 evaluates every element against the guess "everybody pushes its snapshot code"; a flip lists every LATER
+//    element whose inputs it can touch (the 129 offsets a+b, a,b in {0} u dirs_) for the next round, and later rounds only
+//    evaluate their list (by gathering; a dense list first recomputes all summaries).  Element i is right once all
+//    earlier ones are, so the fixpoint -- reached by a round without flips, which has only read final words -- is the
+//    sequential execution.  In BIG mode the summaries of a flipped element's targets are recomputed during the next round.
+//  * Commit: element i owns slot k iff the final state of its k-th target carries the timestamp 32*i + k; the owned slots in
+//    timestamp order (per-element masks, exclusive scan over CTA-contiguous ranges) are the next generation.
+#include <stdio.h>
+#include "fb_common.cuh"
+#include "fb_exact.h"
+
+#define XT 1024                       // threads per CTA, one CTA per SM
+#define XW (XT / 32)
+#define XNONE 0xffffffffu
+#define X_DEAD 0ull
+#define X_PULL 1ull
+#define X_PUSH 2ull
+#define XMB_NONE 0xffffffffffffffffull
+#define X_NOFF 129
+#define XGB 8                         // writer words loaded per batch by a gather (24 / XGB batches)
+#define XDBG_GENS 1024                // trace layout (FIESTA_DEBUG_X): [3 * XDBG_GENS] per generation {nE, rounds, cycles},
+#define XDBG_PHASE (3 * XDBG_GENS)    // then 16 x {cycles, count} per phase category, then 2 x 512 work-list sizes per round
+#define XDBG_ROUNDS (XDBG_PHASE + 32)
+
+static __constant__ int x_dirs[24][3] = {
+    {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
+    {-1, -1, 0}, {1, 1, 0}, {0, -1, -1}, {0, 1, 1}, {-1, 0, -1}, {1, 0, 1},
+    {-1, 1, 0}, {1, -1, 0}, {0, -1, 1}, {0, 1, -1}, {1, 0, -1}, {-1, 0, 1},
+    {-2, 0, 0}, {2, 0, 0}, {0, -2, 0}, {0, 2, 0}, {0, 0, -2}, {0, 0, 2}};
+static __constant__ int x_off_c[X_NOFF];     // the distinct sums a+b, packed (dx+4) | (dy+4)<<4 | (dz+4)<<8 (filled by fb_xrelax_init)
+
+struct XShared {
+  int off[X_NOFF];                    // copy of x_off_c (lane-varying index: shared memory, not the constant cache)
+  int dir[32];                        // dirs_ packed the same way; entry 24 = (0,0,0)
+  unsigned red[XW], red2[XW];
+  unsigned base, total;
+};
+
+__device__ __forceinline__ void x_coords(const FbGeom &g, uint32_t ii, int &x, int &y, int &z) {
+  z = ii % (unsigned)g.pz; const unsigned xy = ii / (unsigned)g.pz; y = xy % (unsigned)g.gy; x = xy / (unsigned)g.gy;
+}
+__device__ __forceinline__ unsigned x_d2(int x, int y, int z, uint32_t c) {
+  int ox, oy, oz; fb_unpack(c, ox, oy, oz); ox -= x; oy -= y; oz -= z;
+  return (unsigned)(ox * ox + oy * oy + oz * oz);
+}
+__device__ __forceinline__ unsigned x_dist_of(int x, int y, int z, uint32_t c) { return c < 2u ? 0xffffffffu : x_d2(x, y, z, c); }
+// packed word: {generation parity:1 | unused:3 | queue position:27 | behaviour:2 | code:31}; all ones = no live entry here
+__device__ __forceinline__ unsigned long long x_mb(unsigned par, unsigned i, unsigned long long kind, uint32_t code) {
+  return ((unsigned long long)(par & 1u) << 63) | ((unsigned long long)i << 33) | (kind << 31) | (unsigned long long)(code & FB_CODE_MASK);
+}
+__device__ __forceinline__ unsigned x_mb_idx(unsigned long long w) { return (unsigned)(w >> 33) & 0x7ffffffu; }
+__device__ __forceinline__ unsigned x_mb_par(unsigned long long w) { return (unsigned)(w >> 63); }
+__device__ __forceinline__ unsigned long long x_mb_kind(unsigned long long w) { return (w >> 31) & 3ull; }
+__device__ __forceinline__ uint32_t x_mb_code(unsigned long long w) { return (uint32_t)(w & FB_CODE_MASK); }
+
+struct XState { unsigned d; uint32_t c; unsigned ts; };
+
+// Everything the kernel reads is written by other SMs between barriers: all loads bypass L1 (ld.global.cg).
+// State of voxel (x,y,z) as seen at time T (exclusive); *first = earliest timestamp of an offer that beats the snapshot.
+template <bool WANT_FIRST>
+__device__ __forceinline__ XState x_gather(const FbGeom &g, const uint32_t *cobs, const unsigned long long *MB, int x, int y, int z, unsigned T,
+                                           unsigned &first, uint32_t &snap) {
+  XState s;
+  const long long v = fb_ii(g, x, y, z);
+  // All loads are issued before anything is decided (the round trip to L2 is what a query costs): the snapshot, the own
+  // word and the first half of the writers' words together, then the second half.
+  const bool inr = fb_in_range(g, x, y, z);                    // pushes only go to voxels inside the update box (:378)
+  unsigned long long w[XGB];
+  const uint32_t snap_raw = __ldcg(&cobs[v]);
+  const unsigned long long wown = __ldcg(&MB[v]);
+#pragma unroll
+  for (int j = 0; j < XGB; ++j) {
+    const int qx = x - x_dirs[j][0], qy = y - x_dirs[j][1], qz = z - x_dirs[j][2];
+    w[j] = (inr && fb_in_grid(g, qx, qy, qz)) ? __ldcg(&MB[fb_ii(g, qx, qy, qz)]) : XMB_NONE;
+  }
+  snap = snap_raw & FB_CODE_MASK;
+  s.c = snap; s.d = x_dist_of(x, y, z, s.c); s.ts = XNONE;
+  first = XNONE;
+  const unsigned d0 = s.d;
+  if (s.c == FB_UNKNOWN) return s;                             // never observed: distance_ = -10000 is never > tmp (:382)
+#pragma unroll
+  for (int h = 0; h < 24 / XGB; ++h) {
+    if (h >= 1) {
+#pragma unroll
+      for (int j = 0; j < XGB; ++j) {
+        const int qx = x - x_dirs[XGB * h + j][0], qy = y - x_dirs[XGB * h + j][1], qz = z - x_dirs[XGB * h + j][2];
+        w[j] = (inr && fb_in_grid(g, qx, qy, qz)) ? __ldcg(&MB[fb_ii(g, qx, qy, qz)]) : XMB_NONE;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < XGB; ++j) {
+      const unsigned long long ww = w[j];
+      if (ww == XMB_NONE || x_mb_kind(ww) != X_PUSH) continue;
+      const unsigned ts = x_mb_idx(ww) * 32u + (unsigned)(XGB * h + j);
+      const uint32_t c = x_mb_code(ww);
+      const unsigned d = x_d2(x, y, z, c);
+      if (d < d0) {
+        if (WANT_FIRST && ts < first) first = ts;
+        if (ts < T && (d < s.d || (d == s.d && ts < s.ts))) { s.d = d; s.c = c; s.ts = ts; }
+      }
+    }
+  }
+  if (wown != XMB_NONE && x_mb_kind(wown) == X_PULL) {         // the entry's own pull is not range-checked (:349-367)
+    const unsigned ts = x_mb_idx(wown) * 32u + 24u;
+    const uint32_t c = x_mb_code(wown);
+    const unsigned d = x_d2(x, y, z, c);
+    if (d < d0) {
+      if (WANT_FIRST && ts < first) first = ts;
+      if (ts < T && (d < s.d || (d == s.d && ts < s.ts))) { s.d = d; s.c = c; s.ts = ts; }
+    }
+  }
+  return s;
+}
+// summary of a target: {first, best timestamp, best code, snapshot code}
+__device__ __forceinline__ void x_summarize(const FbGeom &g, const uint32_t *cobs, const unsigned long long *MB, uint4 *SUM, int x, int y, int z) {
+  unsigned first; uint32_t snap;
+  const XState f = x_gather<true>(g, cobs, MB, x, y, z, XNONE, first, snap);
+  SUM[fb_ii(g, x, y, z)] = make_uint4(first, f.ts, f.c, snap);
+}
+template <bool USE_SUM>
+__device__ __forceinline__ XState x_state(const FbGeom &g, const uint32_t *cobs, const unsigned long long *MB, const uint4 *SUM, int x, int y, int z,
+                                          unsigned T, uint32_t &snap) {
+  unsigned first;
+  if (USE_SUM) {
+    const uint4 u = __ldcg(&SUM[fb_ii(g, x, y, z)]);
+    snap = u.w;
+    XState s;
+    if (u.x == XNONE || T <= u.x) { s.c = u.w; s.d = x_dist_of(x, y, z, s.c); s.ts = XNONE; return s; }
+    if (T > u.y) { s.c = u.z; s.d = x_dist_of(x, y, z, s.c); s.ts = u.y; return s; }
+  }
+  return x_gather<false>(g, cobs, MB, x, y, z, T, first, snap);  // first < T <= best: gather
+}
+
+// ---- grid barrier (all CTAs are co-resident: cooperative launch, one CTA per SM) ---------------------------------------
+__device__ __forceinline__ unsigned x_ld_acquire(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void x_gsync(unsigned *bar, unsigned &target) {
+  // bar.sync orders the CTA's writes before thread 0's release; the release / acquire pair at gpu scope is cumulative, and
+  // every load of shared data in this kernel bypasses L1 (ld.global.cg), so no further fences are needed.
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
+    while (x_ld_acquire(bar) < target) { }
+  }
+  __syncthreads();
+}
+
+struct XArgs {
+  FbGeom g;
+  uint32_t *cobs;
+  unsigned long long *MB, *LS;
+  uint4 *SUM;
+  uint32_t *SUMg;
+  uint32_t *E[2];
+  uint32_t *T;
+  uint32_t *emask;
+  uint32_t *W[3], *F[3];
+  uint32_t *wstamp;
+  uint32_t *slotc;          // SMALL mode: winner codes, [small_max][32]
+  FbXCtl *ctl;
+  unsigned nE0, small_max;  // nE0: insert seeds already in E[0]
+  // E2 (delete loop): dependants of deleted obstacles in the order of the reference's list walk
+  const uint32_t *deps; unsigned ndep;
+  uint32_t *ord;            // per voxel: position in deps, or XNONE
+  uint32_t *nc;             // per dependant: re-seeded code (FB_INF at start)
+  const uint32_t *occbits;
+  unsigned long long ls_deps;   // link time of dependant 0 (InsertIntoList order, :333)
+  unsigned long long *dbg;  // optional per-generation trace {nE, rounds, ns} (FIESTA_DEBUG_X)
+};
+
+__device__ __forceinline__ void x_unpack_off(int o, int &dx, int &dy, int &dz) { dx = (o & 15) - 4; dy = ((o >> 4) & 15) - 4; dz = ((o >> 8) & 15) - 4; }
+
+// New entry r of a generation at voxel v with code c: its word, and (BIG) its targets.  Called by one warp.
+__device__ __forceinline__ void x_begin_entry(const XArgs &a, const XShared &sh, unsigned lane, unsigned r, uint32_t v, uint32_t c, bool big, unsigned gen,
+                                              unsigned *nT) {
+  if (lane == 0) a.MB[v] = x_mb(gen, r, X_PUSH, c);
+  if (!big) return;
+  int x, y, z; x_coords(a.g, v, x, y, z);
+  bool add = false; uint32_t n = 0;
+  if (lane < 25) {
+    int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
+    const int nx = x + dx, ny = y + dy, nz = z + dz;
+    if (fb_in_grid(a.g, nx, ny, nz) && (lane == 24 || fb_in_range(a.g, nx, ny, nz))) {
+      n = (uint32_t)fb_ii(a.g, nx, ny, nz);
+      add = __ldcg(&a.SUMg[n]) != gen && atomicExch(&a.SUMg[n], gen) != gen;
+    }
+  }
+  const unsigned slot = fb_warp_append(nT, add);
+  if (add) a.T[slot] = n;
+}
+
+// Behaviour of element i (one warp; lanes 0..23 = neighbour k at pop time, lane 24 = the element itself).  Returns the new word.
+template <bool USE_SUM>
+__device__ __forceinline__ unsigned long long x_eval(const XArgs &a, const XShared &sh, unsigned lane, unsigned par, unsigned i, uint32_t p, int x, int y, int z) {
+  const FbGeom &g = a.g;
+  const unsigned T0 = i * 32u;
+  int qx = x, qy = y, qz = z;
+  bool valid = lane == 24;
+  if (lane < 24) {
+    int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
+    qx += dx; qy += dy; qz += dz;
+    valid = fb_in_range(g, qx, qy, qz) && fb_in_grid(g, qx, qy, qz);
+  }
+  XState st; st.d = 0xffffffffu; st.c = 0; st.ts = XNONE;
+  uint32_t snap = 0;
+  if (valid) st = x_state<USE_SUM>(g, a.cobs, a.MB, a.SUM, qx, qy, qz, T0, snap);
+  const unsigned sd = __shfl_sync(0xffffffffu, st.d, 24);
+  const uint32_t sc = __shfl_sync(0xffffffffu, st.c, 24);
+  const uint32_t c0 = __shfl_sync(0xffffffffu, snap, 24);
+  if (sd != x_dist_of(x, y, z, c0)) return x_mb(par, i, X_DEAD, 0);   // `xx.distance_ != distance_buffer_[idx]`: stale (:345)
+  unsigned long long key = ~0ull;                              // pull phase (:349-367) = lexicographic minimum (tmp, k) below the own distance
+  if (lane < 24 && valid && st.c >= 2u) {
+    const unsigned t = x_d2(x, y, z, st.c);
+    if (t < sd) key = ((unsigned long long)t << 8) | lane;
+  }
+  unsigned long long best = key;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o); best = other < best ? other : best; }
+  if (best == ~0ull) return x_mb(par, i, X_PUSH, sc);
+  return x_mb(par, i, X_PULL, __shfl_sync(0xffffffffu, st.c, (int)(best & 0xffu)));
+}
+
+// Exclusive scan of one count per thread over the CTA (two block barriers); returns the CTA total in `total`.
+__device__ __forceinline__ unsigned x_block_scan(XShared &sh, unsigned c, unsigned lane, unsigned wid, unsigned &total) {
+  unsigned incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+  __syncthreads();                                             // earlier readers of sh.red are done
+  if (lane == 31) sh.red[wid] = incl;
+  __syncthreads();
+  const unsigned v = sh.red[lane]; unsigned s = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, s, o); if ((int)lane >= o) s += t; }
+  total = __shfl_sync(0xffffffffu, s, 31);
+  return __shfl_sync(0xffffffffu, s - v, (int)wid) + incl - c;
+}
+
+// One evaluation of the re-seeding rule: dependant i takes the closest obstacle of the FIRST neighbour in dirs_ order that
+// has a valid one (:308-321); dependants processed earlier expose their new value, later ones their (deleted) old one.
+__device__ __forceinline__ uint32_t x_reseed_eval(const XArgs &a, unsigned i, int x, int y, int z) {
+  const FbGeom &g = a.g;
+  for (int k = 0; k < 24; ++k) {
+    const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
+    if (!fb_in_range(g, nx, ny, nz) || !fb_in_grid(g, nx, ny, nz)) continue;
+    const long long nv = fb_ii(g, nx, ny, nz);
+    const unsigned o = __ldcg(&a.ord[nv]);
+    uint32_t c;
+    if (o != XNONE) { if (o < i) c = __ldcg(&a.nc[o]); else continue; }
+    else c = __ldcg(&a.cobs[nv]) & FB_CODE_MASK;
+    if (c >= 2u) {
+      int ox, oy, oz; fb_unpack(c, ox, oy, oz);
+      const long long oi = fb_ii(g, ox, oy, oz);
+      if ((__ldg(&a.occbits[oi >> 5]) >> (oi & 31)) & 1u) return c;   // Exist(closest obstacle) (:312), then `break` (:319)
+    }
+  }
+  return FB_INF;
+}
+
+__global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
+  __shared__ XShared sh;
+  const FbGeom &g = a.g;
+  FbXCtl *ctl = a.ctl;
+  const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+  const unsigned G = gridDim.x, b = blockIdx.x;
+  const unsigned gtid = b * XT + tid, gthreads = G * XT;
+  const unsigned gwarp = gtid >> 5, gwarps = gthreads >> 5;
+  for (unsigned k = tid; k < X_NOFF; k += XT) sh.off[k] = x_off_c[k];
+  if (tid < 32) sh.dir[tid] = tid < 24 ? ((x_dirs[tid][0] + 4) | ((x_dirs[tid][1] + 4) << 4) | ((x_dirs[tid][2] + 4) << 8)) : (4 | (4 << 4) | (4 << 8));
+  __syncthreads();
+
+  // grid-uniform state (every CTA computes the same values)
+  unsigned nE = a.nE0, bar_target = 0;
+  int cur = 0;
+  unsigned gen = ctl->gen_id, wclock = ctl->wclock;
+  unsigned long long tclock = ctl->tclock;
+  unsigned generations = 0, rounds_total = 0, dense_total = 0;
+  unsigned long long changed_total = 0;
+  if (a.dbg) {                                                 // cost of an empty grid barrier
+    const long long t0 = clock64();
+    for (int q = 0; q < 32; ++q) x_gsync(&ctl->bar, bar_target);
+    if (gtid == 0) a.dbg[XDBG_PHASE + 2 * 11] = (unsigned long long)(clock64() - t0) / 32ull;
+  }
+  // ---- E2, second half: re-seed the dependants of the deleted obstacles (fixpoint over work lists, in place), then append
+  // the re-seeded ones, in list-walk order, to the insert seeds in E[0] (:301-334).
+  unsigned reseed_rounds = 0;
+  if (a.ndep) {
+    for (unsigned r = 1;; ++r) {
+      const unsigned in = r % 3u, out = (r + 1u) % 3u, zz = (r + 2u) % 3u;
+      const unsigned nw = r == 1u ? a.ndep : __ldcg(&ctl->nW[in]);
+      if (gtid == 0) ctl->nW[zz] = 0;
+      if (r > 1u && nw == 0u) break;
+      ++reseed_rounds; ++wclock;
+      for (unsigned q = gtid; q < nw; q += gthreads) {
+        const unsigned i = r == 1u ? q : __ldcg(&a.W[in][q]);
+        int x, y, z; x_coords(g, __ldcg(&a.deps[i]), x, y, z);
+        const uint32_t res = x_reseed_eval(a, i, x, y, z);
+        if (res == __ldcg(&a.nc[i])) continue;
+        a.nc[i] = res;
+        for (int k = 0; k < 24; ++k) {                         // later dependants that look at this one
+          const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
+          if (!fb_in_grid(g, nx, ny, nz)) continue;
+          const unsigned o = __ldcg(&a.ord[fb_ii(g, nx, ny, nz)]);
+          if (o != XNONE && o > i && __ldcg(&a.wstamp[o]) != wclock && atomicExch(&a.wstamp[o], wclock) != wclock)
+            a.W[out][atomicAdd(&ctl->nW[out], 1u)] = o;
+        }
+      }
+      x_gsync(&ctl->bar, bar_target);
+    }
+    const unsigned per = (a.ndep + G - 1u) / G;
+    const unsigned lo = min(a.ndep, b * per), hi = min(a.ndep, lo + per);
+    unsigned mine = 0;
+    for (unsigned i = lo + tid; i < hi; i += XT) mine += __ldcg(&a.nc[i]) >= 2u ? 1u : 0u;
+    unsigned tot;
+    x_block_scan(sh, mine, lane, wid, tot);
+    if (tid == 0) ctl->partial[b] = tot;
+    if (gtid == 0) { ctl->nW[0] = ctl->nW[1] = ctl->nW[2] = 0; }
+    x_gsync(&ctl->bar, bar_target);
+    if (wid == 0) {
+      unsigned before = 0, all = 0;
+      for (unsigned k = lane; k < G; k += 32u) { const unsigned c = __ldcg(&ctl->partial[k]); all += c; if (k < b) before += c; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); all += __shfl_xor_sync(0xffffffffu, all, o); }
+      if (lane == 0) { sh.base = before; sh.total = all; }
+    }
+    __syncthreads();
+    unsigned run = nE + sh.base;
+    for (unsigned i0 = lo; i0 < hi; i0 += XT) {
+      const unsigned i = i0 + tid;
+      uint32_t c = FB_INF, v = 0;
+      if (i < hi) {
+        c = __ldcg(&a.nc[i]); v = __ldcg(&a.deps[i]);
+        a.cobs[v] = c;
+        a.LS[v] = a.ls_deps + i;                               // InsertIntoList(new_obs_idx, obs_idx) (:333)
+      }
+      unsigned ctot;
+      const unsigned pos = x_block_scan(sh, (i < hi && c >= 2u) ? 1u : 0u, lane, wid, ctot);
+      if (i < hi && c >= 2u) a.E[0][run + pos] = v;            // `if (distance < infinity_) update_queue_.push` (:329-331)
+      run += ctot;
+    }
+    nE += sh.total;
+    x_gsync(&ctl->bar, bar_target);
+  }
+  bool big = nE > a.small_max;
+
+  // generation 0: words + targets
+  ++gen;
+  for (unsigned i = gwarp; i < nE; i += gwarps) {
+    const uint32_t v = __ldcg(&a.E[0][i]);
+    x_begin_entry(a, sh, lane, i, v, __ldcg(&a.cobs[v]) & FB_CODE_MASK, big, gen, &ctl->nT[gen & 1u]);
+  }
+  x_gsync(&ctl->bar, bar_target);
+
+  long long t_ph = a.dbg ? clock64() : 0;
+#define X_LAP(cat) do { if (a.dbg && gtid == 0) { const long long t_now = clock64(); a.dbg[XDBG_PHASE + 2 * (cat)] += (unsigned long long)(t_now - t_ph); a.dbg[XDBG_PHASE + 2 * (cat) + 1] += 1ull; t_ph = t_now; } } while (0)
+  while (nE) {
+    const long long t_gen = a.dbg ? clock64() : 0;
+    X_LAP(10);
+    ++generations;
+    const uint32_t *E = a.E[cur];
+    unsigned nT = 0;
+    if (big) {
+      nT = __ldcg(&ctl->nT[gen & 1u]);
+      for (unsigned t = gtid; t < nT; t += gthreads) { int x, y, z; x_coords(g, __ldcg(&a.T[t]), x, y, z); x_summarize(g, a.cobs, a.MB, a.SUM, x, y, z); }
+      x_gsync(&ctl->bar, bar_target);
+      X_LAP(0);
+    }
+    // ---- behaviour fixpoint
+    unsigned rounds = 0;
+    for (unsigned r = 1;; ++r) {
+      const unsigned in = r % 3u, out = (r + 1u) % 3u, zz = (r + 2u) % 3u;
+      const unsigned nw = r == 1u ? nE : __ldcg(&ctl->nW[in]);
+      const unsigned nf = (big && r > 1u) ? __ldcg(&ctl->nF[in]) : 0u;
+      if (gtid == 0) { ctl->nW[zz] = 0; ctl->nF[zz] = 0; }
+      if (r > 1u && nw == 0u && nf == 0u) break;
+      ++rounds; ++wclock;
+      const bool dense = big && r > 1u && nw > nE / 8u;
+      if (dense) {
+        ++dense_total;
+        for (unsigned t = gtid; t < nT; t += gthreads) { int x, y, z; x_coords(g, __ldcg(&a.T[t]), x, y, z); x_summarize(g, a.cobs, a.MB, a.SUM, x, y, z); }
+        x_gsync(&ctl->bar, bar_target);
+      }
+      const bool use_sum = big && (r == 1u || dense);
+      const unsigned nref = (big && !dense) ? nf : 0u;
+      const uint32_t *wl = a.W[in];
+      for (unsigned q = gwarp; q < nw + nref; q += gwarps) {
+        if (q >= nw) {                                         // summaries of the targets of an element that flipped last round
+          const unsigned i = __ldcg(&a.F[in][q - nw]);
+          int x, y, z; x_coords(g, __ldcg(&E[i]), x, y, z);
+          if (lane < 25) {
+            int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
+            const int nx = x + dx, ny = y + dy, nz = z + dz;
+            if (fb_in_grid(g, nx, ny, nz) && (lane == 24 || fb_in_range(g, nx, ny, nz))) x_summarize(g, a.cobs, a.MB, a.SUM, nx, ny, nz);
+          }
+          continue;
+        }
+        const unsigned i = r == 1u ? q : __ldcg(&wl[q]);
+        const uint32_t p = __ldcg(&E[i]);
+        int x, y, z; x_coords(g, p, x, y, z);
+        unsigned long long old = 0;
+        if (lane == 0) old = __ldcg(&a.MB[p]);
+        const unsigned long long nb = use_sum ? x_eval<true>(a, sh, lane, gen, i, p, x, y, z) : x_eval<false>(a, sh, lane, gen, i, p, x, y, z);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (nb == old) continue;
+        if (lane == 0) {                                       // flip
+          a.MB[p] = nb;
+          if (big) a.F[out][atomicAdd(&ctl->nF[out], 1u)] = i;
+        }
+        for (unsigned o = lane; o < X_NOFF; o += 32u) {        // later elements whose inputs this element can touch
+          int dx, dy, dz; x_unpack_off(sh.off[o], dx, dy, dz);
+          const int nx = x + dx, ny = y + dy, nz = z + dz;
+          bool push = false; unsigned j = 0;
+          if (fb_in_grid(g, nx, ny, nz)) {
+            const unsigned long long w = __ldcg(&a.MB[fb_ii(g, nx, ny, nz)]);
+            if (w != XMB_NONE) {
+              j = x_mb_idx(w);
+              push = j > i && __ldcg(&a.wstamp[j]) != wclock && atomicExch(&a.wstamp[j], wclock) != wclock;
+            }
+          }
+          const unsigned slot = fb_warp_append(&ctl->nW[out], push);
+          if (push) a.W[out][slot] = j;
+        }
+      }
+      x_gsync(&ctl->bar, bar_target);
+      X_LAP(big ? (r == 1u ? 1 : (dense ? 3 : 2)) : (r == 1u ? 6 : 7));
+      if (a.dbg && gtid == 0 && generations <= 2u && r <= 512u) a.dbg[XDBG_ROUNDS + (generations - 1u) * 512u + (r - 1u)] = nw;
+    }
+    rounds_total += rounds;
+
+    // ---- commit: per-element masks of owned slots, winner counts per CTA (CTA-contiguous ranges keep the order)
+    const unsigned per = (nE + G - 1u) / G;
+    const unsigned lo = min(nE, b * per), hi = min(nE, lo + per);
+    unsigned wcount = 0, wlive = 0;
+    for (unsigned i = lo + wid; i < hi; i += XW) {
+      const uint32_t p = __ldcg(&E[i]);
+      int x, y, z; x_coords(g, p, x, y, z);
+      unsigned long long w = 0;
+      if (lane == 0) w = __ldcg(&a.MB[p]);
+      w = __shfl_sync(0xffffffffu, w, 0);
+      const unsigned long long kind = x_mb_kind(w);
+      bool win = false;
+      if ((kind == X_PUSH && lane < 24) || (kind == X_PULL && lane == 24)) {
+        int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
+        const int nx = x + dx, ny = y + dy, nz = z + dz;
+        if (fb_in_grid(g, nx, ny, nz) && (lane == 24 || fb_in_range(g, nx, ny, nz))) {
+          const unsigned ts = i * 32u + lane;
+          if (big) win = __ldcg(&a.SUM[fb_ii(g, nx, ny, nz)]).y == ts;
+          else {
+            unsigned first; uint32_t snap;
+            const XState f = x_gather<false>(g, a.cobs, a.MB, nx, ny, nz, XNONE, first, snap);
+            win = f.ts == ts;
+            if (win) a.slotc[ts] = f.c;
+          }
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, win);
+      if (lane == 0) { a.emask[i] = m; wcount += __popc(m); wlive += kind != X_DEAD ? 1u : 0u; }
+    }
+    // (the words of this generation are retired in the apply phase: SMALL-mode commits still gather from them here)
+    if (lane == 0) { sh.red[wid] = wcount; sh.red2[wid] = wlive; }
+    __syncthreads();
+    if (wid == 0) {
+      unsigned c = sh.red[lane], l = sh.red2[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, o); l += __shfl_xor_sync(0xffffffffu, l, o); }
+      if (lane == 0) { ctl->partial[b] = c; if (l) atomicAdd(&ctl->expansions, (unsigned long long)l); }   // `times++` (:347)
+    }
+    if (gtid == 0) { ctl->nT[(gen + 1u) & 1u] = 0; ctl->nW[0] = ctl->nW[1] = ctl->nW[2] = 0; ctl->nF[0] = ctl->nF[1] = ctl->nF[2] = 0; }
+    x_gsync(&ctl->bar, bar_target);
+    X_LAP(big ? 4 : 8);
+
+    // ---- apply: exclusive scan of the counts -> queue positions of the next generation; words + targets of the new entries
+    if (wid == 0) {
+      unsigned before = 0, all = 0;
+      for (unsigned k = lane; k < G; k += 32u) { const unsigned c = __ldcg(&ctl->partial[k]); all += c; if (k < b) before += c; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); all += __shfl_xor_sync(0xffffffffu, all, o); }
+      if (lane == 0) { sh.base = before; sh.total = all; }
+    }
+    __syncthreads();
+    const unsigned n2 = sh.total;
+    const bool big2 = n2 > a.small_max;
+    uint32_t *En = a.E[cur ^ 1];
+    unsigned run = sh.base;                                    // queue position of the first winner of the current chunk
+    for (unsigned i0 = lo; i0 < hi; i0 += XT) {
+      const unsigned i = i0 + tid;
+      const uint32_t m = i < hi ? __ldcg(&a.emask[i]) : 0u;
+      if (i < hi) {                                            // retire the old entry's word unless a new entry already replaced it
+        const uint32_t p = __ldcg(&E[i]);
+        const unsigned long long w = __ldcg(&a.MB[p]);
+        if (w != XMB_NONE && x_mb_par(w) == (gen & 1u)) atomicCAS(&a.MB[p], w, XMB_NONE);
+      }
+      const unsigned c = __popc(m);
+      unsigned incl = c;                                       // inclusive warp scan
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+      __syncthreads();                                         // previous chunk's readers of sh.red are done
+      if (lane == 31) sh.red[wid] = incl;
+      __syncthreads();
+      unsigned wbase = 0, ctot = 0;
+      { const unsigned v = sh.red[lane]; unsigned s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, s, o); if ((int)lane >= o) s += t; }
+        wbase = __shfl_sync(0xffffffffu, s - v, (int)wid); ctot = __shfl_sync(0xffffffffu, s, 31); }
+      const unsigned excl = run + wbase + incl - c;
+      // the warp walks its 32 elements; every winner is one warp step
+      unsigned any = __ballot_sync(0xffffffffu, c != 0u);
+      while (any) {
+        const int e = __ffs(any) - 1; any &= any - 1u;
+        uint32_t me = __shfl_sync(0xffffffffu, m, e);
+        unsigned r = __shfl_sync(0xffffffffu, excl, e);
+        const unsigned ie = i0 + wid * 32u + (unsigned)e;
+        const uint32_t p = __ldcg(&E[ie]);
+        int x, y, z; x_coords(g, p, x, y, z);
+        while (me) {
+          const int k = __ffs(me) - 1; me &= me - 1u;
+          int dx, dy, dz; x_unpack_off(sh.dir[k], dx, dy, dz);
+          const uint32_t v = (uint32_t)fb_ii(g, x + dx, y + dy, z + dz);
+          const unsigned ts = ie * 32u + (unsigned)k;
+          uint32_t code = 0;
+          if (lane == 0) code = big ? __ldcg(&a.SUM[v]).z : __ldcg(&a.slotc[ts]);
+          code = __shfl_sync(0xffffffffu, code, 0);
+          if (lane == 0) {
+            a.cobs[v] = code;
+            a.LS[v] = tclock + ts;                             // every accepted write relinks the voxel at its list's front (:24-42)
+            En[r] = v;
+          }
+          x_begin_entry(a, sh, lane, r, v, code, big2, gen + 1u, &ctl->nT[(gen + 1u) & 1u]);
+          ++r;
+        }
+      }
+      run += ctot;
+    }
+    if (a.dbg && gtid == 0 && generations <= 1024u) { a.dbg[3 * (generations - 1u)] = nE; a.dbg[3 * (generations - 1u) + 1] = rounds; a.dbg[3 * (generations - 1u) + 2] = (unsigned long long)(clock64() - t_gen); }
+    tclock += (unsigned long long)nE * 32ull + 1ull;
+    changed_total += n2;
+    if (n2 >= (1u << 27)) { if (gtid == 0) ctl->err = 1u; break; }
+    const bool was_big = big;
+    nE = n2; cur ^= 1; big = big2; ++gen;
+    x_gsync(&ctl->bar, bar_target);
+    X_LAP(was_big ? 5 : 9);
+  }
+  if (gtid == 0) {
+    ctl->gen_id = gen; ctl->wclock = wclock; ctl->tclock = tclock;
+    ctl->generations = generations; ctl->reseed_rounds = reseed_rounds; ctl->rounds = rounds_total; ctl->dense_rounds = dense_total; ctl->voxels_changed = changed_total;
+  }
+}
+
+static bool g_off_ready = false;
+cudaError_t fb_xrelax_init() {
+  if (g_off_ready) return cudaSuccess;
+  static const int D[24][3] = {
+      {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
+      {-1, -1, 0}, {1, 1, 0}, {0, -1, -1}, {0, 1, 1}, {-1, 0, -1}, {1, 0, 1},
+      {-1, 1, 0}, {1, -1, 0}, {0, -1, 1}, {0, 1, -1}, {1, 0, -1}, {-1, 0, 1},
+      {-2, 0, 0}, {2, 0, 0}, {0, -2, 0}, {0, 2, 0}, {0, 0, -2}, {0, 0, 2}};
+  int off[1024], n = 0;
+  for (int p = -1; p < 24; ++p)
+    for (int q = -1; q < 24; ++q) {
+      int o[3];
+      for (int k = 0; k < 3; ++k) o[k] = (p < 0 ? 0 : D[p][k]) + (q < 0 ? 0 : D[q][k]);
+      const int code = (o[0] + 4) | ((o[1] + 4) << 4) | ((o[2] + 4) << 8);
+      bool dup = false;
+      for (int j = 0; j < n; ++j) dup = dup || off[j] == code;
+      if (!dup) off[n++] = code;
+    }
+  if (n != X_NOFF) return cudaErrorUnknown;
+  cudaError_t e = cudaMemcpyToSymbol(x_off_c, off, sizeof(int) * X_NOFF);
+  if (e == cudaSuccess) g_off_ready = true;
+  return e;
+}
+
+int fb_xrelax_blocks(int device) {
+  int per_sm = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_x_relax, XT, 0) != cudaSuccess || per_sm < 1) return -1;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
+  return sms;                                                  // one CTA per SM: the barrier is cheapest with few arrivals
+}
+
+cudaError_t fb_xrelax_launch(FbExact *X, const FbGeom &g, uint32_t *cobs, unsigned nE0, const uint32_t *deps, unsigned ndep, uint32_t *ord, uint32_t *nc,
+                             const uint32_t *occbits, unsigned long long ls_deps, unsigned long long *dbg, cudaStream_t s) {
+  XArgs a;
+  a.deps = deps; a.ndep = ndep; a.ord = ord; a.nc = nc; a.occbits = occbits; a.ls_deps = ls_deps;
+  a.g = g; a.cobs = cobs; a.MB = X->MB; a.LS = X->LS; a.SUM = X->SUM; a.SUMg = X->SUMg;
+  a.E[0] = X->E[0]; a.E[1] = X->E[1]; a.T = X->T; a.emask = X->emask;
+  for (int k = 0; k < 3; ++k) { a.W[k] = X->W[k]; a.F[k] = X->F[k]; }
+  a.wstamp = X->wstamp; a.slotc = X->slotc; a.ctl = X->d_ctl; a.nE0 = nE0; a.small_max = X->small_max; a.dbg = dbg;
+  void *args[] = {(void *)&a};
+  return cudaLaunchCooperativeKernel((void *)k_x_relax, dim3(X->relax_blocks), dim3(XT), args, 0, s);
+}
