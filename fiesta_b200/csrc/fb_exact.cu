@@ -188,7 +188,7 @@ cudaError_t fb_exact_init(FbExact *X, const FbGeom &g, int device, cudaStream_t 
   XCK(cudaMalloc((void **)&X->MB, P * 8)); XCK(cudaMalloc((void **)&X->LS, P * 8)); XCK(cudaMalloc((void **)&X->tkey, P * 8));
   XCK(cudaMalloc((void **)&X->touched, P * 4));
   XCK(cudaMalloc((void **)&X->SUM, P * 16)); XCK(cudaMalloc((void **)&X->SUMg, P * 4)); XCK(cudaMemsetAsync(X->SUMg, 0, P * 4, s));
-  XCK(cudaMalloc((void **)&X->T, P * 4)); XCK(cudaMalloc((void **)&X->emask, P * 4));
+  XCK(cudaMalloc((void **)&X->emask, P * 4));
   XCK(cudaMalloc((void **)&X->wstamp, P * 4)); XCK(cudaMemsetAsync(X->wstamp, 0, P * 4, s));
   for (int k = 0; k < 3; ++k) { XCK(cudaMalloc((void **)&X->W[k], P * 4)); XCK(cudaMalloc((void **)&X->F[k], P * 4)); }
   for (int k = 0; k < 2; ++k) { XCK(cudaMalloc((void **)&X->E[k], P * 4)); X->cap_E[k] = P; }
@@ -203,11 +203,11 @@ cudaError_t fb_exact_init(FbExact *X, const FbGeom &g, int device, cudaStream_t 
   k_x_fill64<<<148 * 8, 256, 0, s>>>(X->MB, P, XMB_NONE);
   k_x_fill64<<<148 * 8, 256, 0, s>>>(X->tkey, P, ~0ull);
   XCK(cudaMemsetAsync(X->LS, 0, P * 8, s));
-  X->tclock = 1; X->key_base = 0; X->gen_id = 0; X->wclock = 0;
+  X->tclock = 1; X->key_base = 0; X->gen_id = 0; X->wclock = 0; X->sclock = 0;
   return cudaGetLastError();
 }
 void fb_exact_free(FbExact *X) {
-  void *p[] = {X->MB, X->LS, X->tkey, X->touched, X->SUM, X->SUMg, X->T, X->emask, X->wstamp, X->W[0], X->W[1], X->W[2], X->F[0], X->F[1], X->F[2], X->slotc,
+  void *p[] = {X->MB, X->LS, X->tkey, X->touched, X->SUM, X->SUMg, X->emask, X->wstamp, X->W[0], X->W[1], X->W[2], X->F[0], X->F[1], X->F[2], X->slotc,
                X->d_ctl, X->d_dbg, X->d_count, X->d_flag, X->E[0], X->E[1], X->sel,
                X->k1, X->k2, X->k1b, X->k2b, X->dv, X->idx[0], X->idx[1], X->deps, X->nc[0], X->nc[1], X->flags, X->flags2, X->cub_tmp};
   for (void *q : p) if (q) cudaFree(q);
@@ -331,18 +331,19 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
   if (nE || ndep_run) {
     if (xdbg && !X->d_dbg) XCK(cudaMalloc((void **)&X->d_dbg, FB_X_DBG_WORDS * 8));
     if (xdbg) XCK(cudaMemsetAsync(X->d_dbg, 0, FB_X_DBG_WORDS * 8, s));
-    if (X->gen_id > 0xf0000000u) { XCK(cudaMemsetAsync(X->SUMg, 0, P * 4, s)); X->gen_id = 0; }       // stamp wrap-around
+    if (X->sclock > 0xf0000000u) { XCK(cudaMemsetAsync(X->SUMg, 0, P * 4, s)); X->sclock = 0; }       // stamp wrap-around
+    if (X->gen_id > 0xf0000000u) X->gen_id = 0;
     if (X->wclock > 0xf0000000u) { XCK(cudaMemsetAsync(X->wstamp, 0, P * 4, s)); X->wclock = 0; }
     FbXCtl *h = X->h_ctl;
     memset(h, 0, sizeof(*h));
-    h->gen_id = X->gen_id; h->wclock = X->wclock; h->tclock = X->tclock;
+    h->gen_id = X->gen_id; h->wclock = X->wclock; h->tclock = X->tclock; h->sclock = X->sclock;
     XCK(cudaMemcpyAsync(X->d_ctl, h, sizeof(FbXCtl), cudaMemcpyHostToDevice, s));
     XCK(fb_xrelax_launch(X, g, cobs, nE, X->deps, ndep_run, scratch, X->nc[0], occbits, ls_deps, xdbg ? X->d_dbg : nullptr, s));
     XCK(cudaMemcpyAsync(h, X->d_ctl, sizeof(FbXCtl), cudaMemcpyDeviceToHost, s));
     XCK(cudaStreamSynchronize(s));
     *launches += 1;
     if (h->err) { snprintf(X->err, sizeof(X->err), "exact mode: generation with more than 2^27 entries"); return cudaErrorInvalidValue; }
-    X->gen_id = h->gen_id; X->wclock = h->wclock; X->tclock = h->tclock;
+    X->gen_id = h->gen_id; X->wclock = h->wclock; X->tclock = h->tclock; X->sclock = h->sclock;
     st->generations = h->generations; st->reseed_rounds = h->reseed_rounds; st->eval_rounds = h->rounds; st->dense_rounds = h->dense_rounds;
     st->voxels_changed = h->voxels_changed; st->expansions = h->expansions;
     if (xdbg) {

@@ -16,7 +16,7 @@ struct FbExactStats {
 // Control block of k_x_relax (device memory; the host writes it before and reads it after every launch).
 struct FbXCtl {
   unsigned bar, err;                  // grid barrier arrivals; 1 = a generation exceeded 2^27 entries
-  unsigned nT[2];                     // target-list length by generation parity
+  unsigned sclock, pad1;              // stamp of the last summary pass (SUMg dedupe; persists across launches)
   unsigned nW[3], nF[3];              // work / flip list lengths, rotating per round
   unsigned gen_id, wclock;            // stamps for SUMg / wstamp dedupe (persist across launches)
   unsigned generations, rounds, dense_rounds, reseed_rounds;
@@ -33,9 +33,8 @@ struct FbExact {
   unsigned long long key_base; // observation clock
   unsigned *d_count, *d_flag, *h_count;
   uint4 *SUM;                  // per voxel offer summary of the current generation: {first ts, best ts, best code, snapshot code}
-  uint32_t *SUMg;              // per voxel: generation id for which the voxel is already in the target list
-  unsigned gen_id, wclock;
-  uint32_t *T;                 // targets of the current generation (BIG generations)
+  uint32_t *SUMg;              // per voxel: summary pass for which SUM was computed (each target is claimed once per pass)
+  unsigned gen_id, wclock, sclock;
   uint32_t *emask;             // per entry: slots it owns in the next generation
   uint32_t *W[3], *F[3];       // work lists / flip lists, rotating per round
   uint32_t *wstamp;            // per entry: round for which it is already in a work list

@@ -29,6 +29,7 @@
 #define X_PUSH 2ull
 #define XMB_NONE 0xffffffffffffffffull
 #define X_NOFF 129
+#define X_DENSE_MIN 4096u
 #define XGB 8                         // writer words loaded per batch by a gather (24 / XGB batches)
 #define XDBG_GENS 1024                // trace layout (FIESTA_DEBUG_X): [3 * XDBG_GENS] per generation {nE, rounds, cycles},
 #define XDBG_PHASE (3 * XDBG_GENS)    // then 16 x {cycles, count} per phase category, then 2 x 512 work-list sizes per round
@@ -168,7 +169,6 @@ struct XArgs {
   uint4 *SUM;
   uint32_t *SUMg;
   uint32_t *E[2];
-  uint32_t *T;
   uint32_t *emask;
   uint32_t *W[3], *F[3];
   uint32_t *wstamp;
@@ -186,23 +186,15 @@ struct XArgs {
 
 __device__ __forceinline__ void x_unpack_off(int o, int &dx, int &dy, int &dz) { dx = (o & 15) - 4; dy = ((o >> 4) & 15) - 4; dz = ((o >> 8) & 15) - 4; }
 
-// New entry r of a generation at voxel v with code c: its word, and (BIG) its targets.  Called by one warp.
-__device__ __forceinline__ void x_begin_entry(const XArgs &a, const XShared &sh, unsigned lane, unsigned r, uint32_t v, uint32_t c, bool big, unsigned gen,
-                                              unsigned *nT) {
-  if (lane == 0) a.MB[v] = x_mb(gen, r, X_PUSH, c);
-  if (!big) return;
-  int x, y, z; x_coords(a.g, v, x, y, z);
-  bool add = false; uint32_t n = 0;
-  if (lane < 25) {
-    int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
-    const int nx = x + dx, ny = y + dy, nz = z + dz;
-    if (fb_in_grid(a.g, nx, ny, nz) && (lane == 24 || fb_in_range(a.g, nx, ny, nz))) {
-      n = (uint32_t)fb_ii(a.g, nx, ny, nz);
-      add = __ldcg(&a.SUMg[n]) != gen && atomicExch(&a.SUMg[n], gen) != gen;
-    }
-  }
-  const unsigned slot = fb_warp_append(nT, add);
-  if (add) a.T[slot] = n;
+// Summaries of the targets of element i (one warp; lane k = target k): whoever first stamps a target for this summary pass
+// (`sclock`, unique per pass) computes it, so every target is summarised exactly once without a target list.
+__device__ __forceinline__ void x_claim_summaries(const XArgs &a, const XShared &sh, unsigned lane, int x, int y, int z, unsigned sclock) {
+  if (lane >= 25u) return;
+  int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
+  const int nx = x + dx, ny = y + dy, nz = z + dz;
+  if (!fb_in_grid(a.g, nx, ny, nz) || !(lane == 24u || fb_in_range(a.g, nx, ny, nz))) return;
+  const long long n = fb_ii(a.g, nx, ny, nz);
+  if (__ldcg(&a.SUMg[n]) != sclock && atomicExch(&a.SUMg[n], sclock) != sclock) x_summarize(a.g, a.cobs, a.MB, a.SUM, nx, ny, nz);
 }
 
 // Behaviour of element i (one warp; lanes 0..23 = neighbour k at pop time, lane 24 = the element itself).  Returns the new word.
@@ -316,8 +308,9 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
           const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
           if (!fb_in_grid(g, nx, ny, nz)) continue;
           const unsigned o = __ldcg(&a.ord[fb_ii(g, nx, ny, nz)]);
-          if (o != XNONE && o > i && __ldcg(&a.wstamp[o]) != wclock && atomicExch(&a.wstamp[o], wclock) != wclock)
-            a.W[out][atomicAdd(&ctl->nW[out], 1u)] = o;
+          const bool push = o != XNONE && o > i && __ldcg(&a.wstamp[o]) != wclock && atomicExch(&a.wstamp[o], wclock) != wclock;
+          const unsigned slot2 = fb_warp_append(&ctl->nW[out], push);
+          if (push) a.W[out][slot2] = o;
         }
       }
       x_gsync(&ctl->bar, bar_target);
@@ -358,11 +351,15 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
   }
   bool big = nE > a.small_max;
 
-  // generation 0: words + targets
+  // generation 0: words.  Initial guess of the fixpoint: every entry pushes its snapshot code.
+  // (Tried and dropped, both bit-exact: a silent start for the re-seeded dependants -- same number of rounds; resolving a
+  // generation window by window in queue order -- the dependency chains of the sweep after a delete are short and local, so
+  // windows only serialise work that the whole-generation rounds do concurrently: 2983 rounds instead of 919.)
   ++gen;
-  for (unsigned i = gwarp; i < nE; i += gwarps) {
+  unsigned sclock = ctl->sclock;
+  for (unsigned i = gtid; i < nE; i += gthreads) {
     const uint32_t v = __ldcg(&a.E[0][i]);
-    x_begin_entry(a, sh, lane, i, v, __ldcg(&a.cobs[v]) & FB_CODE_MASK, big, gen, &ctl->nT[gen & 1u]);
+    a.MB[v] = x_mb(gen, i, X_PUSH, __ldcg(&a.cobs[v]) & FB_CODE_MASK);
   }
   x_gsync(&ctl->bar, bar_target);
 
@@ -373,15 +370,14 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
     X_LAP(10);
     ++generations;
     const uint32_t *E = a.E[cur];
-    unsigned nT = 0;
+    // ---- behaviour fixpoint
+    unsigned rounds = 0;
     if (big) {
-      nT = __ldcg(&ctl->nT[gen & 1u]);
-      for (unsigned t = gtid; t < nT; t += gthreads) { int x, y, z; x_coords(g, __ldcg(&a.T[t]), x, y, z); x_summarize(g, a.cobs, a.MB, a.SUM, x, y, z); }
+      ++sclock;
+      for (unsigned i = gwarp; i < nE; i += gwarps) { int x, y, z; x_coords(g, __ldcg(&E[i]), x, y, z); x_claim_summaries(a, sh, lane, x, y, z, sclock); }
       x_gsync(&ctl->bar, bar_target);
       X_LAP(0);
     }
-    // ---- behaviour fixpoint
-    unsigned rounds = 0;
     for (unsigned r = 1;; ++r) {
       const unsigned in = r % 3u, out = (r + 1u) % 3u, zz = (r + 2u) % 3u;
       const unsigned nw = r == 1u ? nE : __ldcg(&ctl->nW[in]);
@@ -389,10 +385,22 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
       if (gtid == 0) { ctl->nW[zz] = 0; ctl->nF[zz] = 0; }
       if (r > 1u && nw == 0u && nf == 0u) break;
       ++rounds; ++wclock;
-      const bool dense = big && r > 1u && nw > nE / 8u;
-      if (dense) {
+      const bool dense = big && r > 1u && nw > X_DENSE_MIN;   // more than one wave of warps: evaluate through the summaries
+      if (dense) {                                             // bring the summaries up to date first, then evaluate through them
         ++dense_total;
-        for (unsigned t = gtid; t < nT; t += gthreads) { int x, y, z; x_coords(g, __ldcg(&a.T[t]), x, y, z); x_summarize(g, a.cobs, a.MB, a.SUM, x, y, z); }
+        if (nf < nE / 4u) {                                    // few flips: only the targets of last round's flips
+          for (unsigned q = gwarp; q < nf; q += gwarps) {
+            int x, y, z; x_coords(g, __ldcg(&E[__ldcg(&a.F[in][q])]), x, y, z);
+            if (lane < 25) {
+              int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
+              const int nx = x + dx, ny = y + dy, nz = z + dz;
+              if (fb_in_grid(g, nx, ny, nz) && (lane == 24 || fb_in_range(g, nx, ny, nz))) x_summarize(g, a.cobs, a.MB, a.SUM, nx, ny, nz);
+            }
+          }
+        } else {
+          ++sclock;
+          for (unsigned i = gwarp; i < nE; i += gwarps) { int x, y, z; x_coords(g, __ldcg(&E[i]), x, y, z); x_claim_summaries(a, sh, lane, x, y, z, sclock); }
+        }
         x_gsync(&ctl->bar, bar_target);
       }
       const bool use_sum = big && (r == 1u || dense);
@@ -438,7 +446,7 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
       }
       x_gsync(&ctl->bar, bar_target);
       X_LAP(big ? (r == 1u ? 1 : (dense ? 3 : 2)) : (r == 1u ? 6 : 7));
-      if (a.dbg && gtid == 0 && generations <= 2u && r <= 512u) a.dbg[XDBG_ROUNDS + (generations - 1u) * 512u + (r - 1u)] = nw;
+      if (a.dbg && gtid == 0 && generations <= 2u && rounds <= 512u) a.dbg[XDBG_ROUNDS + (generations - 1u) * 512u + (rounds - 1u)] = nw;
     }
     rounds_total += rounds;
 
@@ -480,7 +488,7 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
       for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, o); l += __shfl_xor_sync(0xffffffffu, l, o); }
       if (lane == 0) { ctl->partial[b] = c; if (l) atomicAdd(&ctl->expansions, (unsigned long long)l); }   // `times++` (:347)
     }
-    if (gtid == 0) { ctl->nT[(gen + 1u) & 1u] = 0; ctl->nW[0] = ctl->nW[1] = ctl->nW[2] = 0; ctl->nF[0] = ctl->nF[1] = ctl->nF[2] = 0; }
+    if (gtid == 0) { ctl->nW[0] = ctl->nW[1] = ctl->nW[2] = 0; ctl->nF[0] = ctl->nF[1] = ctl->nF[2] = 0; }
     x_gsync(&ctl->bar, bar_target);
     X_LAP(big ? 4 : 8);
 
@@ -505,42 +513,22 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
         const unsigned long long w = __ldcg(&a.MB[p]);
         if (w != XMB_NONE && x_mb_par(w) == (gen & 1u)) atomicCAS(&a.MB[p], w, XMB_NONE);
       }
-      const unsigned c = __popc(m);
-      unsigned incl = c;                                       // inclusive warp scan
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
-      __syncthreads();                                         // previous chunk's readers of sh.red are done
-      if (lane == 31) sh.red[wid] = incl;
-      __syncthreads();
-      unsigned wbase = 0, ctot = 0;
-      { const unsigned v = sh.red[lane]; unsigned s = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, s, o); if ((int)lane >= o) s += t; }
-        wbase = __shfl_sync(0xffffffffu, s - v, (int)wid); ctot = __shfl_sync(0xffffffffu, s, 31); }
-      const unsigned excl = run + wbase + incl - c;
-      // the warp walks its 32 elements; every winner is one warp step
-      unsigned any = __ballot_sync(0xffffffffu, c != 0u);
-      while (any) {
-        const int e = __ffs(any) - 1; any &= any - 1u;
-        uint32_t me = __shfl_sync(0xffffffffu, m, e);
-        unsigned r = __shfl_sync(0xffffffffu, excl, e);
-        const unsigned ie = i0 + wid * 32u + (unsigned)e;
-        const uint32_t p = __ldcg(&E[ie]);
+      unsigned ctot;
+      unsigned r = run + x_block_scan(sh, (unsigned)__popc(m), lane, wid, ctot);
+      if (m) {                                                 // this thread's element owns slots: records, link times, words of the new entries
+        const uint32_t p = __ldcg(&E[i]);
         int x, y, z; x_coords(g, p, x, y, z);
+        uint32_t me = m;
         while (me) {
           const int k = __ffs(me) - 1; me &= me - 1u;
           int dx, dy, dz; x_unpack_off(sh.dir[k], dx, dy, dz);
           const uint32_t v = (uint32_t)fb_ii(g, x + dx, y + dy, z + dz);
-          const unsigned ts = ie * 32u + (unsigned)k;
-          uint32_t code = 0;
-          if (lane == 0) code = big ? __ldcg(&a.SUM[v]).z : __ldcg(&a.slotc[ts]);
-          code = __shfl_sync(0xffffffffu, code, 0);
-          if (lane == 0) {
-            a.cobs[v] = code;
-            a.LS[v] = tclock + ts;                             // every accepted write relinks the voxel at its list's front (:24-42)
-            En[r] = v;
-          }
-          x_begin_entry(a, sh, lane, r, v, code, big2, gen + 1u, &ctl->nT[(gen + 1u) & 1u]);
+          const unsigned ts = i * 32u + (unsigned)k;
+          const uint32_t code = big ? __ldcg(&a.SUM[v]).z : __ldcg(&a.slotc[ts]);
+          a.cobs[v] = code;
+          a.LS[v] = tclock + ts;                               // every accepted write relinks the voxel at its list's front (:24-42)
+          En[r] = v;
+          a.MB[v] = x_mb(gen + 1u, r, X_PUSH, code);
           ++r;
         }
       }
@@ -556,7 +544,7 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
     X_LAP(was_big ? 5 : 9);
   }
   if (gtid == 0) {
-    ctl->gen_id = gen; ctl->wclock = wclock; ctl->tclock = tclock;
+    ctl->gen_id = gen; ctl->wclock = wclock; ctl->tclock = tclock; ctl->sclock = sclock;
     ctl->generations = generations; ctl->reseed_rounds = reseed_rounds; ctl->rounds = rounds_total; ctl->dense_rounds = dense_total; ctl->voxels_changed = changed_total;
   }
 }
@@ -597,7 +585,7 @@ cudaError_t fb_xrelax_launch(FbExact *X, const FbGeom &g, uint32_t *cobs, unsign
   XArgs a;
   a.deps = deps; a.ndep = ndep; a.ord = ord; a.nc = nc; a.occbits = occbits; a.ls_deps = ls_deps;
   a.g = g; a.cobs = cobs; a.MB = X->MB; a.LS = X->LS; a.SUM = X->SUM; a.SUMg = X->SUMg;
-  a.E[0] = X->E[0]; a.E[1] = X->E[1]; a.T = X->T; a.emask = X->emask;
+  a.E[0] = X->E[0]; a.E[1] = X->E[1]; a.emask = X->emask;
   for (int k = 0; k < 3; ++k) { a.W[k] = X->W[k]; a.F[k] = X->F[k]; }
   a.wstamp = X->wstamp; a.slotc = X->slotc; a.ctl = X->d_ctl; a.nE0 = nE0; a.small_max = X->small_max; a.dbg = dbg;
   void *args[] = {(void *)&a};

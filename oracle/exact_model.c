@@ -15,9 +15,10 @@
 //             gathers when first < T <= best.
 //   round 1 evaluates every element; a flip (behaviour change) lists every LATER element whose inputs it can touch
 //             (the 129 offsets a+b, a,b in {0} u dirs) for the next round and, in BIG mode, is itself listed so that
-//             the summaries of its targets are recomputed during the next round.  Rounds after the first evaluate by
-//             gathering (summaries may be stale there) unless the work list is dense, in which case all summaries are
-//             recomputed first.  The fixpoint is reached by a round without flips: it has read final words only.
+//             the summaries of its targets are recomputed.  Short work lists are evaluated by gathering while last round's
+//             flips are refreshed concurrently; long ones first bring the summaries up to date (targets of the flips, or
+//             everything when most entries flipped) and then evaluate through them.  The fixpoint is reached by a round
+//             without flips: it has read final words only.
 //   commit: element i owns slot k iff the final state of its target k carries timestamp 32*i+k; the owned slots in
 //             timestamp order are the next generation (per-element masks + exclusive scan).
 #include <stdio.h>
@@ -54,7 +55,7 @@ static inline u32 mb_idx(u64 w){return (u32)(w>>33);} static inline u64 mb_kind(
 
 typedef struct {u32 d,c,ts;} st_t;
 typedef struct {u32 first,best_ts,best_c,snap_c;} sum_t;
-static sum_t *SUM; static u32 *SUMg; static u32 gen_id=0;
+static sum_t *SUM; static u32 *SUMg;
 static long n_gather=0,n_query=0;
 // State of voxel v as seen at time T (exclusive): gather over the <= 25 writers.
 static st_t gather(int x,int y,int z,u32 T,u32*first){
@@ -91,116 +92,62 @@ static u64 eval(long i,int use_sum){
 static int OFF[1024][3]; static int nOFF=0;
 static void build_offsets(void){ for(int a=-1;a<24;a++)for(int b=-1;b<24;b++){ int o[3]; for(int q=0;q<3;q++)o[q]=(a<0?0:DIRS[a][q])+(b<0?0:DIRS[b][q]);
   int dup=0; for(int j=0;j<nOFF;j++) if(OFF[j][0]==o[0]&&OFF[j][1]==o[1]&&OFF[j][2]==o[2])dup=1; if(!dup){OFF[nOFF][0]=o[0];OFF[nOFF][1]=o[1];OFF[nOFF][2]=o[2];nOFF++;} } }
-static u32 *W[3]; static long nW[3]; static u32 *wstamp; static u32 wclock=0;
+static u32 *W[3]; static long nW[3]; static u32 *F[3]; static long nF[3]; static u32 *wstamp; static u32 wclock=0;
 static void shuffle(u32*a,long n){ for(long i=n-1;i>0;i--){ long j=rand()%(i+1); u32 t=a[i];a[i]=a[j];a[j]=t; } }
-static long expansions; static long totrounds=0, totgens=0, maxrounds=0, totevals=0, totvisits=0, totpasses=0;
-static u32 *emask, *ecode;
-// ---- BIG generations: tile mode.  The grid is cut into 8^3 tiles; a visit stages the tile + a 4-voxel halo (16^3 words and
-// codes), finds the tile's entries in the staged words, iterates them to a LOCAL fixpoint (dirty bits; flips are written to
-// the staged copy and to the global words), computes the slot masks of all its entries from the staged copy, and lists the
-// neighbour tiles within reach (4 voxels) of a flip for the next round.  A round without flips has staged final words only.
-static int TX,TY,TZ; static u32 *tstamp,*dstamp; static u32 *AT[2]; static long nAT[2]; static u32 *DT[3]; static long nDT[3];
-static int MAXPASS=4;
-typedef struct { u64 mb[4096]; u32 cb[4096]; int ox,oy,oz; } stage_t;
-static inline int sidx(int lx,int ly,int lz){return (lx*16+ly)*16+lz;}
-static void stage(stage_t*S,int t){ int tz=t%TZ,ty=(t/TZ)%TY,tx=t/(TZ*TY); S->ox=8*tx-4;S->oy=8*ty-4;S->oz=8*tz-4;
-  for(int lx=0;lx<16;lx++)for(int ly=0;ly<16;ly++)for(int lz=0;lz<16;lz++){ int x=S->ox+lx,y=S->oy+ly,z=S->oz+lz; int k=sidx(lx,ly,lz);
-    if(ing(x,y,z)){S->mb[k]=MB[vi(x,y,z)];S->cb[k]=C[vi(x,y,z)];} else {S->mb[k]=MB_NONE;S->cb[k]=CU;} } }
-static st_t gather_l(const stage_t*S,int x,int y,int z,u32 T){   // gather() on the staged copy (global coordinates)
-  st_t s; int lx=x-S->ox,ly=y-S->oy,lz=z-S->oz; s.c=S->cb[sidx(lx,ly,lz)]; s.d=dcode(x,y,z,s.c); s.ts=NONE; u32 d0=s.d;
-  if(s.c==CU) return s;
-  if(inb(x,y,z))
-  for(int k=0;k<24;k++){ int qx=lx-DIRS[k][0],qy=ly-DIRS[k][1],qz=lz-DIRS[k][2]; if(qx<0||qy<0||qz<0||qx>15||qy>15||qz>15){printf("stage reach\n");exit(1);}
-    u64 w=S->mb[sidx(qx,qy,qz)]; if(w==MB_NONE||mb_kind(w)!=K_PUSH) continue; u32 ts=mb_idx(w)*32+k; u32 c=mb_code(w); u32 d=d2(x,y,z,c);
-    if(d<d0&&ts<T&&(d<s.d||(d==s.d&&ts<s.ts))){s.d=d;s.c=c;s.ts=ts;} }
-  u64 w=S->mb[sidx(lx,ly,lz)]; if(w!=MB_NONE&&mb_kind(w)==K_PULL){ u32 ts=mb_idx(w)*32+24; u32 c=mb_code(w); u32 d=d2(x,y,z,c);
-    if(d<d0&&ts<T&&(d<s.d||(d==s.d&&ts<s.ts))){s.d=d;s.c=c;s.ts=ts;} }
-  return s;
-}
-static u64 eval_l(const stage_t*S,u32 i,int x,int y,int z){
-  u32 T0=i*32; st_t s=gather_l(S,x,y,z,T0); u32 d0=dcode(x,y,z,S->cb[sidx(x-S->ox,y-S->oy,z-S->oz)]);
-  if(s.d!=d0) return mbw(i,K_DEAD,0);
-  u32 curd=s.d,curc=s.c; int ch=0;
-  for(int k=0;k<24;k++){ int nx=x+DIRS[k][0],ny=y+DIRS[k][1],nz=z+DIRS[k][2]; if(!ing(nx,ny,nz)||!inb(nx,ny,nz)) continue;
-    st_t sn=gather_l(S,nx,ny,nz,T0); if(sn.c<2) continue; u32 t=d2(x,y,z,sn.c); if(curd>t){curd=t;curc=sn.c;ch=1;} }
-  return ch?mbw(i,K_PULL,curc):mbw(i,K_PUSH,s.c);
-}
-static void mark_tile(u32 t,int out){ if(dstamp[t]!=wclock){ dstamp[t]=wclock; DT[out][nDT[out]++]=t; } }
-// one visit; returns the number of flips
-static long visit(stage_t*S,int t,int out){
-  int tz=t%TZ,ty=(t/TZ)%TY,tx=t/(TZ*TY); totvisits++;
-  static u32 el[512]; int nel=0; unsigned char dirty[512],next[512]; memset(dirty,0,512);
-  for(int j=0;j<512;j++){ int lx=4+(j>>6),ly=4+((j>>3)&7),lz=4+(j&7); u64 w=S->mb[sidx(lx,ly,lz)]; if(w!=MB_NONE){ el[nel++]=j; dirty[j]=1; } }
-  long flips=0; u32 nbmask=0; int left=nel;
-  for(int pass=0;pass<MAXPASS&&left;pass++){ totpasses++; memset(next,0,512); left=0;
-    u32 ord[512]; int no=0; for(int q=0;q<nel;q++) if(dirty[el[q]]) ord[no++]=el[q]; shuffle(ord,no);
-    for(int q=0;q<no;q++){ int j=ord[q]; int lx=4+(j>>6),ly=4+((j>>3)&7),lz=4+(j&7); int x=S->ox+lx,y=S->oy+ly,z=S->oz+lz; u64 w=S->mb[sidx(lx,ly,lz)]; u32 i=mb_idx(w); totevals++;
-      u64 nb=eval_l(S,i,x,y,z);
-      if(nb!=w){ S->mb[sidx(lx,ly,lz)]=nb; MB[vi(x,y,z)]=nb; flips++;
-        for(int o=0;o<nOFF;o++){ int qx=lx+OFF[o][0],qy=ly+OFF[o][1],qz=lz+OFF[o][2]; if(qx<4||qy<4||qz<4||qx>11||qy>11||qz>11) continue;
-          u64 w2=S->mb[sidx(qx,qy,qz)]; if(w2!=MB_NONE&&mb_idx(w2)>i){ int j2=((qx-4)<<6)|((qy-4)<<3)|(qz-4); if(!next[j2]){next[j2]=1;left++;} } }
-        int dx=(lx-4)<=3?-1:1,dy=(ly-4)<=3?-1:1,dz=(lz-4)<=3?-1:1;
-        for(int sx=0;sx<2;sx++)for(int sy=0;sy<2;sy++)for(int sz=0;sz<2;sz++){ if(!(sx|sy|sz)) continue; int ax=1+sx*dx,ay=1+sy*dy,az=1+sz*dz; nbmask|=1u<<((ax*3+ay)*3+az); } } }
-    memcpy(dirty,next,512); }
-  if(left) mark_tile((u32)t,out);                      // pass budget exhausted: come back next round
-  for(int q=0;q<nel;q++){ int j=el[q]; int lx=4+(j>>6),ly=4+((j>>3)&7),lz=4+(j&7); int x=S->ox+lx,y=S->oy+ly,z=S->oz+lz; u64 b=S->mb[sidx(lx,ly,lz)]; u32 i=mb_idx(b); u32 m=0;
-    if(mb_kind(b)==K_PUSH){ for(int k=0;k<24;k++){ int nx=x+DIRS[k][0],ny=y+DIRS[k][1],nz=z+DIRS[k][2]; if(!ing(nx,ny,nz)||!inb(nx,ny,nz)) continue; st_t f=gather_l(S,nx,ny,nz,NONE); if(f.ts==i*32+k) m|=1u<<k; } }
-    else if(mb_kind(b)==K_PULL){ st_t f=gather_l(S,x,y,z,NONE); if(f.ts==i*32+24) m|=1u<<24; }
-    emask[i]=m; }
-  for(int a=0;a<27;a++) if(nbmask>>a&1){ int ax=a/9-1,ay=(a/3)%3-1,az=a%3-1; int nx=tx+ax,ny=ty+ay,nz=tz+az; if(nx<0||ny<0||nz<0||nx>=TX||ny>=TY||nz>=TZ) continue; u32 nt=(u32)((nx*TY+ny)*TZ+nz);
-      if(tstamp[nt]==gen_id) mark_tile(nt,out); }
-  return flips;
-}
-static void begin_entry(long r,long v,u32 c,int big,int par){   // new entry r of a generation at voxel v with code c
-  MB[v]=mbw((u32)r,K_PUSH,c);
-  if(big){ int x,y,z; vxyz(v,&x,&y,&z); u32 t=(u32)(((x>>3)*TY+(y>>3))*TZ+(z>>3)); if(tstamp[t]!=gen_id){ tstamp[t]=gen_id; AT[par][nAT[par]++]=t; } }
-}
+static long expansions; static long totrounds=0, totgens=0, maxrounds=0, totevals=0, totdense=0;
+static u32 *emask; static u32 *slotc;   // slotc: SMALL mode only
+static long DENSE_MIN=16;               // work lists longer than this are evaluated through the summaries (kernel: 4096)
+static u32 sclock=0;
+// summaries of the targets of element i; every target is summarised once per pass (stamp sclock in SUMg)
+static void claim_summaries(long i){ long p=E[cur][i]; int x,y,z; vxyz(p,&x,&y,&z);
+  for(int k=0;k<25;k++){ int nx=k<24?x+DIRS[k][0]:x,ny=k<24?y+DIRS[k][1]:y,nz=k<24?z+DIRS[k][2]:z; if(!ing(nx,ny,nz)||(k<24&&!inb(nx,ny,nz))) continue;
+    long n=vi(nx,ny,nz); if(SUMg[n]!=sclock){ SUMg[n]=sclock; summarize(nx,ny,nz); } } }
+static void refresh_targets(long i){ long p=E[cur][i]; int x,y,z; vxyz(p,&x,&y,&z);
+  for(int k=0;k<25;k++){ int nx=k<24?x+DIRS[k][0]:x,ny=k<24?y+DIRS[k][1]:y,nz=k<24?z+DIRS[k][2]:z; if(!ing(nx,ny,nz)||(k<24&&!inb(nx,ny,nz))) continue; summarize(nx,ny,nz); } }
 static void relax(void){
-  int big=nE>SMALL; gen_id++; nAT[gen_id&1]=0;
-  for(long i=0;i<nE;i++) begin_entry(i,E[cur][i],C[E[cur][i]],big,gen_id&1);
+  int big=nE>SMALL;
+  for(long i=0;i<nE;i++) MB[E[cur][i]]=mbw((u32)i,K_PUSH,C[E[cur][i]]);   // initial guess: everybody pushes its snapshot code
   while(nE){
     totgens++;
-    int rounds=0; nW[0]=nW[1]=nW[2]=0; nDT[0]=nDT[1]=nDT[2]=0;
+    if(big){ sclock++; u32*ord=malloc(4*(nE+1)); for(long i=0;i<nE;i++)ord[i]=(u32)i; shuffle(ord,nE); for(long q=0;q<nE;q++) claim_summaries(ord[q]); free(ord); }
+    int rounds=0; nW[0]=nW[1]=nW[2]=0; nF[0]=nF[1]=nF[2]=0;
     for(int r=1;;r++){
-      int in=r%3,out=(r+1)%3; nW[(r+2)%3]=0; nDT[(r+2)%3]=0; wclock++;
-      if(big){
-        long nt=r==1?nAT[gen_id&1]:nDT[in]; u32*tl=r==1?AT[gen_id&1]:DT[in];
-        if(r>1&&nt==0) break;
-        rounds++; shuffle(tl,nt);
-        int pre=rand()&1;                                  // stage every tile at the start of the round (stalest legal view) or when it is visited
-        stage_t*SS=pre?malloc(sizeof(stage_t)*nt):malloc(sizeof(stage_t)); if(pre) for(long q=0;q<nt;q++) stage(&SS[q],tl[q]);
-        for(long q=0;q<nt;q++){ if(!pre) stage(&SS[0],tl[q]); visit(pre?&SS[q]:&SS[0],tl[q],out); }
-        free(SS);
-      } else {
-        long nw; u32*wl=W[in];
-        if(r==1){ nw=nE; for(long i=0;i<nE;i++)wl[i]=(u32)i; } else nw=nW[in];
-        if(r>1&&nw==0) break;
-        rounds++; shuffle(wl,nw);
-        for(long q=0;q<nw;q++){ long i=wl[q]; totevals++;
-          u64 nb=eval(i,0); long p=E[cur][i];
-          if(nb!=MB[p]){ MB[p]=nb;
-            int x,y,z; vxyz(p,&x,&y,&z);
-            for(int o=0;o<nOFF;o++){ int nx=x+OFF[o][0],ny=y+OFF[o][1],nz=z+OFF[o][2]; if(!ing(nx,ny,nz)) continue; u64 w=MB[vi(nx,ny,nz)]; if(w==MB_NONE) continue; u32 j=mb_idx(w);
-              if(j>(u32)i && wstamp[j]!=wclock){ wstamp[j]=wclock; W[out][nW[out]++]=j; } } } }
-      }
+      int in=r%3,out=(r+1)%3; nW[(r+2)%3]=0; nF[(r+2)%3]=0; wclock++;
+      long nw; u32*wl=W[in];
+      if(r==1){ nw=nE; for(long i=0;i<nE;i++)wl[i]=(u32)i; } else nw=nW[in];
+      long nf=(big&&r>1)?nF[in]:0;
+      if(r>1&&nw==0&&nf==0) break;
+      rounds++;
+      int dense=big&&r>1&&nw>DENSE_MIN; int use_sum=big&&(r==1||dense);
+      if(dense){ totdense++;     // summaries first (targets of last round's flips, or everything), then evaluate through them
+        if(nf<nE/4){ for(long q=0;q<nf;q++) refresh_targets(F[in][q]); } else { sclock++; for(long i=0;i<nE;i++) claim_summaries(i); } }
+      // this round's work: evaluations and (big, not dense) summary refreshes of last round's flips, randomly interleaved
+      long nref=(big&&!dense)?nf:0; long tot=nw+nref; u32*ord=malloc(4*(tot+1)); for(long q=0;q<tot;q++)ord[q]=(u32)q; shuffle(ord,tot);
+      for(long q=0;q<tot;q++){ long a=ord[q];
+        if(a>=nw){ refresh_targets(F[in][a-nw]); continue; }
+        long i=wl[a]; totevals++;
+        u64 nb=eval(i,use_sum); long p=E[cur][i];
+        if(nb!=MB[p]){ MB[p]=nb; if(big) F[out][nF[out]++]=(u32)i;
+          int x,y,z; vxyz(p,&x,&y,&z);
+          for(int o=0;o<nOFF;o++){ int nx=x+OFF[o][0],ny=y+OFF[o][1],nz=z+OFF[o][2]; if(!ing(nx,ny,nz)) continue; u64 w=MB[vi(nx,ny,nz)]; if(w==MB_NONE) continue; u32 j=mb_idx(w);
+            if(j>(u32)i && wstamp[j]!=wclock){ wstamp[j]=wclock; W[out][nW[out]++]=j; } } } }
+      free(ord);
       if(rounds>100000){printf("no convergence\n");exit(1);} }
     totrounds+=rounds; if(rounds>maxrounds)maxrounds=rounds;
-    // count phase: SMALL generations compute their slot masks here (by gathering); every entry's code and liveness are taken from its final word
+    // commit: slot masks
     long total=0;
-    for(long i=0;i<nE;i++){ long p=E[cur][i]; u64 b=MB[p]; int x,y,z; vxyz(p,&x,&y,&z);
+    for(long i=0;i<nE;i++){ u64 b=MB[E[cur][i]]; u32 m=0; long p=E[cur][i]; int x,y,z; vxyz(p,&x,&y,&z);
       if(mb_kind(b)!=K_DEAD) expansions++;
-      ecode[i]=mb_code(b);
-      if(!big){ u32 m=0;
-        if(mb_kind(b)==K_PUSH){ for(int k=0;k<24;k++){ int nx=x+DIRS[k][0],ny=y+DIRS[k][1],nz=z+DIRS[k][2]; if(!ing(nx,ny,nz)||!inb(nx,ny,nz)) continue; st_t f=gather(nx,ny,nz,NONE,NULL); if(f.ts==(u32)i*32+k) m|=1u<<k; } }
-        else if(mb_kind(b)==K_PULL){ st_t f=gather(x,y,z,NONE,NULL); if(f.ts==(u32)i*32+24) m|=1u<<24; }
-        emask[i]=m; }
-      total+=__builtin_popcount(emask[i]); }
+      if(mb_kind(b)==K_PUSH){ for(int k=0;k<24;k++){ int nx=x+DIRS[k][0],ny=y+DIRS[k][1],nz=z+DIRS[k][2]; if(!ing(nx,ny,nz)||!inb(nx,ny,nz)) continue; u32 ts=(u32)i*32+k;
+          if(big){ sum_t u=SUM[vi(nx,ny,nz)]; if(u.best_ts==ts) m|=1u<<k; } else { st_t f=gather(nx,ny,nz,NONE,NULL); if(f.ts==ts){ m|=1u<<k; slotc[i*32+k]=f.c; } } } }
+      else if(mb_kind(b)==K_PULL){ u32 ts=(u32)i*32+24; if(big){ sum_t u=SUM[p]; if(u.best_ts==ts) m|=1u<<24; } else { st_t f=gather(x,y,z,NONE,NULL); if(f.ts==ts){ m|=1u<<24; slotc[i*32+24]=f.c; } } }
+      emask[i]=m; total+=__builtin_popcount(m); }
     for(long i=0;i<nE;i++) MB[E[cur][i]]=MB_NONE;    // (kernel: retired by compare-and-swap in the apply phase)
-    // apply: exclusive scan of the mask popcounts -> positions; an owned slot carries the code its owner offered
-    int big2=total>SMALL; gen_id++; nAT[gen_id&1]=0; long r=0;
+    // apply: exclusive scan of the mask popcounts -> positions
+    int big2=total>SMALL; long r=0;
     for(long i=0;i<nE;i++){ long p=E[cur][i]; int x,y,z; vxyz(p,&x,&y,&z); u32 m=emask[i];
       for(int k=0;k<25;k++) if(m>>k&1){ int nx=k<24?x+DIRS[k][0]:x,ny=k<24?y+DIRS[k][1]:y,nz=k<24?z+DIRS[k][2]:z; long v=vi(nx,ny,nz);
-          u32 c=ecode[i]; C[v]=c; LS[v]=tclock+(u64)i*32+k; E[cur^1][r]=(u32)v; begin_entry(r,v,c,big2,gen_id&1); r++; } }
+          u32 c=big?SUM[v].best_c:slotc[i*32+k]; C[v]=c; LS[v]=tclock+(u64)i*32+k; E[cur^1][r]=(u32)v; MB[v]=mbw((u32)r,K_PUSH,c); r++; } }
     tclock+=(u64)nE*32+1; nE=r; cur^=1; big=big2;
   }
 }
@@ -212,10 +159,9 @@ int main(int argc,char**argv){
   int local=argc>7?atoi(argv[7]):0;   // 1: shrink the update box for the later rounds (SetUpdateRange)
   double org[3]={0,0,0},sz[3]={G*0.1-0.05,G*0.1-0.05,G*0.1-0.05}; O=fiesta_oracle_create(org,0.1,sz); fiesta_oracle_set_parameters(O,0.97,0.03,0.30,0.90,0.80);
   GX=O->gs[0];GY=O->gs[1];GZ=O->gs[2];N=(long)GX*GY*GZ; C=calloc(N,4); MB=malloc(N*8); LS=calloc(N,8); for(long i=0;i<N;i++)MB[i]=MB_NONE;
-  if(argc>8) MAXPASS=atoi(argv[8]);
-  emask=malloc(4*N); ecode=malloc(4*N);
-  E[0]=malloc(4*N);E[1]=malloc(4*N); for(int q=0;q<3;q++){W[q]=malloc(4*N);} wstamp=calloc(N,4);
-  TX=(GX+7)/8;TY=(GY+7)/8;TZ=(GZ+7)/8; long NTL=(long)TX*TY*TZ; tstamp=calloc(NTL,4);dstamp=calloc(NTL,4); for(int q=0;q<2;q++)AT[q]=malloc(4*NTL); for(int q=0;q<3;q++)DT[q]=malloc(4*NTL);
+  if(argc>8) DENSE_MIN=atol(argv[8]);
+  SUM=calloc(N,sizeof(sum_t)); SUMg=calloc(N,4); emask=malloc(4*N); slotc=malloc(4*32*(SMALL+1));
+  E[0]=malloc(4*N);E[1]=malloc(4*N); for(int q=0;q<3;q++){W[q]=malloc(4*N);F[q]=malloc(4*N);} wstamp=calloc(N,4);
   build_offsets(); if(nOFF!=129){printf("offsets %d\n",nOFF);return 1;}
   long bad=0;
   for(int r=0;r<rounds;r++){
@@ -252,7 +198,7 @@ int main(int argc,char**argv){
     relax();
     long dm=0,cm=0; for(long i=0;i<N;i++){ u32 c=C[i]; double d; int x,y,z; vxyz(i,&x,&y,&z); if(c==CU)d=-10000; else if(c==CI)d=10000; else d=sqrt((double)d2(x,y,z,c))*0.1;
       if(d!=O->dist[i])dm++; int ox=-10000,oy=-10000,oz=-10000; if(c>=2)unpack(c,&ox,&oy,&oz); if(ox!=O->cobs[3*i]||oy!=O->cobs[3*i+1]||oz!=O->cobs[3*i+2])cm++; }
-    printf("[gens %ld rounds %ld max %ld evals %ld visits %ld passes %ld | gathers %ld] round %d ins %ld del %ld dep %ld | ref expansions %ld ours %ld | dist mismatches %ld cobs mismatches %ld\n",totgens,totrounds,maxrounds,totevals,totvisits,totpasses,n_gather,r,nins,ndel,ndep,O->st_exp,expansions,dm,cm);
+    printf("[gens %ld rounds %ld max %ld evals %ld dense %ld | queries %ld gathers %ld] round %d ins %ld del %ld dep %ld | ref expansions %ld ours %ld | dist mismatches %ld cobs mismatches %ld\n",totgens,totrounds,maxrounds,totevals,totdense,n_query,n_gather,r,nins,ndel,ndep,O->st_exp,expansions,dm,cm);
     if(dm||cm||O->st_exp!=expansions) bad++;
     free(pred);free(ins);free(del);free(rank);free(deps);free(ord);free(nc0);free(nc1);
   }
