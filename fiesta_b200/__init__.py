@@ -97,14 +97,14 @@ def _f64(a):
 class ESDFMap:
     """Mirror of fiesta::ESDFMap (ESDFMap.h:111-164); every method forwards 1:1 to the C ABI."""
 
-    def __init__(self, origin, resolution, map_size, device=0, mode="fast"):
+    def __init__(self, origin, resolution, map_size, device=0, mode="exact"):
         self._L = load_library()
         cfg = Config()
         cfg.origin = D3(*origin)
         cfg.resolution = float(resolution)
         cfg.map_size = D3(*map_size)
         cfg.device = int(device)
-        cfg.mode = {"fast": 0, "exact": 1}[mode]
+        cfg.mode = {"exact": 0, "fast": 1}[mode]             # FIESTA_MODE_EXACT / FIESTA_MODE_FAST
         self.mode = mode
         h = C.c_void_p()
         rc = self._L.fiesta_create(C.byref(cfg), C.byref(h))

@@ -29,6 +29,10 @@
 #define FB_BOXZ (FB_TILE + 2 * FB_ZPAD)           // 16   starts at z0 - 4 (not z0 - 2) and is 16 voxels long in z
 #define FB_BOX_WORDS (FB_BOX * FB_BOX * FB_BOXZ)  // 2304
 #define FB_FRESH 0x80000000u
+// EXACT mode (which never uses FRESH) keeps in the same bit, between calls, "distance_ forced to +infinity_ while the closest
+// obstacle and its dependant-list link are kept" -- the state UpdateOccupancy(false) leaves behind for a voxel outside the
+// previous update box (ESDFMap.cpp:256-259).  Cleared by the next write of the record.
+#define FB_DINF 0x80000000u
 #define FB_CODE_MASK 0x7fffffffu
 #define FB_MAX_GX 2046
 #define FB_MAX_GY 1024

@@ -65,7 +65,10 @@ __global__ void k_x_integrate(FbGeom g, const uint32_t *vox, unsigned n, unsigne
   const bool was = o > l_occ;
   const bool skip = (upd >= 0 && o >= l_max) || (upd <= 0 && o <= l_min);
   if (!skip) {
-    if (!global_map) { int x, y, z; x_coords(g, ii, x, y, z); if (!fb_in_last_range(g, x, y, z)) { o = 0; cobs[ii] = FB_INF; } }
+    if (!global_map) {                                          // local map (:256-259): occupancy 0, distance_ +infinity_, closest obstacle KEPT
+      int x, y, z; x_coords(g, ii, x, y, z);
+      if (!fb_in_last_range(g, x, y, z)) { o = 0; if ((cobs[ii] & FB_CODE_MASK) >= 2u) cobs[ii] |= FB_DINF; }
+    }
     double s = o + upd;
     s = s > l_min ? s : l_min;
     s = s < l_max ? s : l_max;

@@ -161,9 +161,10 @@ __global__ void __launch_bounds__(128) k_integrate(FbGeom g, const uint32_t *til
 
 // distance_buffer_ value of a record (ESDFMap.cpp:122-123, 198, 247): exact because the stored obstacle coordinate is exact.
 __device__ __forceinline__ double fb_record_distance(uint32_t c, int x, int y, int z, double res) {
+  const bool dinf = (c & FB_DINF) != 0u;                                    // between calls bit 31 is only ever set by EXACT mode's local-map reset
   c &= FB_CODE_MASK;
   if (c == FB_UNKNOWN) return (double)FIESTA_UNDEFINED;
-  if (c == FB_INF) return (double)FIESTA_INFINITY;
+  if (c == FB_INF || dinf) return (double)FIESTA_INFINITY;
   int ox, oy, oz;
   fb_unpack(c, ox, oy, oz);
   const double dx = (double)(ox - x), dy = (double)(oy - y), dz = (double)(oz - z);
@@ -347,7 +348,10 @@ int fiesta_create(const fiesta_config *cfg, fiesta_map **out) {
   if (!m) { set_error("out of host memory"); return FIESTA_ERR_INVALID; }
   memset((void *)m, 0, sizeof(*m));
   m->device = cfg->device;
-  m->mode = cfg->mode == FIESTA_MODE_EXACT ? FIESTA_MODE_EXACT : FIESTA_MODE_FAST;
+  m->mode = cfg->mode == FIESTA_MODE_FAST ? FIESTA_MODE_FAST : FIESTA_MODE_EXACT;
+  if (const char *em = getenv("FIESTA_B200_MODE")) {                    // documented override (include/fiesta_b200.h)
+    if (!strcmp(em, "fast")) m->mode = FIESTA_MODE_FAST; else if (!strcmp(em, "exact")) m->mode = FIESTA_MODE_EXACT;
+  }
   m->shard_rank = 0; m->shard_world = 1;
   FbGeom &g = m->g;
   int gs[3];
@@ -438,10 +442,12 @@ int fiesta_grid_size(const fiesta_map *m, int out[3]) {
 
 int fiesta_set_occupancy_vox(fiesta_map *m, const int vox[3], int occ) {
   int ret = FIESTA_UNDEFINED;
+  if (!m || !vox) return FIESTA_UNDEFINED;
   if (host_set_occupancy_vox(m, vox, occ, &ret) != FIESTA_OK) return FIESTA_UNDEFINED;
   return ret;
 }
 int fiesta_set_occupancy_pos(fiesta_map *m, const double pos[3], int occ) {
+  if (!m || !pos) return FIESTA_UNDEFINED;
   if (occ != 1 && occ != 0) return FIESTA_UNDEFINED;                      // "occ value error!", ESDFMap.cpp:402-405
   if (!host_pos_in_map(m->g, pos)) return FIESTA_UNDEFINED;               // :407-410
   int v[3];
@@ -489,9 +495,10 @@ int fiesta_set_occupancy_batch_vox_device(fiesta_map *m, const int *d_vox, const
 
 int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, const double T[16], const fiesta_raycast_params *p) {
   if (!m || !T || !p || n < 0 || (n > 0 && !d_xyz)) { set_error("fiesta_raycast_frame: bad argument"); return FIESTA_ERR_INVALID; }
-  if (n >= (int64_t)FB_RAY_MASK) { set_error("fiesta_raycast_frame: more than 2^20-1 points per frame"); return FIESTA_ERR_LIMIT; }
+  if (n >= (int64_t)FB_RAY_MASK) { set_error("fiesta_raycast_frame: more than 2^19-2 (524286) points per frame"); return FIESTA_ERR_LIMIT; }
   CK(cudaSetDevice(m->device));
   m->st.rays_cast = m->st.rays_dropped = m->st.ray_voxels = m->st.raycast_rounds = 0; m->st.ms_raycast = 0;
+  { int fr = flush_events(m); if (fr) return fr; }                         // per-call SetOccupancy events issued before this frame come first in occupancy_queue_
   if (n == 0) return FIESTA_OK;
   const FbGeom &g = m->g;
   FbRayArgs a;
@@ -722,6 +729,11 @@ int fiesta_update_esdf(fiesta_map *m) {
   CK(cudaEventRecord(m->ev[2], m->stream));
   CK(fb_esdf_wavefront(m->g, a, m->tmap, m->wf_blocks, m->stream));                                           // E3
   m->st.kernel_launches++;
+  if (m->shard_world > 1) {                                               // FRESH flags the seed / delete scan left in the ghost layers
+    const int x0 = m->tile_x_lo * 8, x1 = m->tile_x_hi * 8 < m->g.gx ? m->tile_x_hi * 8 : m->g.gx;
+    if (m->shard_rank > 0) CK(fb_esdf_halo_retire(m->g, m->cobs, x0 - 2, 2, m->stream));
+    if (m->shard_rank + 1 < m->shard_world) CK(fb_esdf_halo_retire(m->g, m->cobs, x1, 2, m->stream));
+  }
   k_reset_queues<<<1, 1, 0, m->stream>>>(m->d_ctr, 0, 1);
   m->st.kernel_launches++;
   CK(cudaEventRecord(m->ev[3], m->stream));
@@ -803,6 +815,7 @@ double fiesta_get_distance_vox(fiesta_map *m, const int vox[3]) {
   if (v[0] == vox[0] && v[1] == vox[1] && v[2] == vox[2] && host_pos_in_map(g, p)) return fiesta_get_distance_pos(m, p);
   uint32_t c = 0;                                                         // pathological origin/resolution: read the record directly
   if (cudaMemcpy(&c, m->cobs + fb_ii(g, vox[0], vox[1], vox[2]), 4, cudaMemcpyDeviceToHost) != cudaSuccess) return FIESTA_INFINITY;
+  if (c & FB_DINF) return FIESTA_INFINITY;
   c &= FB_CODE_MASK;
   if (c < 2u) return FIESTA_INFINITY;
   int ox, oy, oz; fb_unpack(c, ox, oy, oz);
@@ -878,6 +891,10 @@ int fiesta_set_shard(fiesta_map *m, int rank, int world, fiesta_shard_info *out)
   if (!m || world < 1 || rank < 0 || rank >= world) { set_error("fiesta_set_shard: bad rank/world"); return FIESTA_ERR_INVALID; }
   if (m->mode != FIESTA_MODE_FAST) { set_error("fiesta_set_shard: sharding is implemented for FIESTA_MODE_FAST only"); return FIESTA_ERR_INVALID; }
   if (world > m->g.tx) { set_error("fiesta_set_shard: more ranks than 8-voxel tile columns"); return FIESTA_ERR_LIMIT; }
+  for (int r = 0; r < world; ++r) {                                       // every slab exchanges 2 x-layers per internal face
+    const int lo = (int)((long long)m->g.tx * r / world) * 8, hi = (int)((long long)m->g.tx * (r + 1) / world) * 8;
+    if ((hi < m->g.gx ? hi : m->g.gx) - lo < 2) { set_error("fiesta_set_shard: a slab would be thinner than the 2-layer ghost exchanged per face (too many ranks for grid_x)"); return FIESTA_ERR_LIMIT; }
+  }
   m->shard_rank = rank; m->shard_world = world;
   m->tile_x_lo = (int)((long long)m->g.tx * rank / world);
   m->tile_x_hi = (int)((long long)m->g.tx * (rank + 1) / world);

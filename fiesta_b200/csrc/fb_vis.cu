@@ -22,9 +22,9 @@ __global__ void k_vis_occ_points(FbGeom g, const uint32_t *sel, unsigned n, floa
   for (int k = 0; k < 3; ++k) out[3 * i + k] = (float)((v[k] + 0.5) * g.res + g.origin[k]);   // Vox2Pos (:79-82), Point32 is float
 }
 __device__ __forceinline__ double fb_slice_dist(const FbGeom &g, const uint32_t *cobs, int x, int y, int z) {
-  const uint32_t c = cobs[fb_ii(g, x, y, z)] & FB_CODE_MASK;
+  const uint32_t raw = cobs[fb_ii(g, x, y, z)], c = raw & FB_CODE_MASK;
   if (c == FB_UNKNOWN) return -10000.0;
-  if (c == FB_INF) return 10000.0;
+  if (c == FB_INF || (raw & FB_DINF)) return 10000.0;
   int ox, oy, oz; fb_unpack(c, ox, oy, oz);
   const double dx = (double)(ox - x), dy = (double)(oy - y), dz = (double)(oz - z);
   return sqrt((dx * dx + dy * dy) + dz * dz) * g.res;

@@ -87,7 +87,7 @@ __device__ __forceinline__ XState x_gather(const FbGeom &g, const uint32_t *cobs
     w[j] = (inr && fb_in_grid(g, qx, qy, qz)) ? __ldcg(&MB[fb_ii(g, qx, qy, qz)]) : XMB_NONE;
   }
   snap = snap_raw & FB_CODE_MASK;
-  s.c = snap; s.d = x_dist_of(x, y, z, s.c); s.ts = XNONE;
+  s.c = snap; s.d = (snap_raw & FB_DINF) ? 0xffffffffu : x_dist_of(x, y, z, s.c); s.ts = XNONE;   // FB_DINF: distance_ forced to +infinity_ (:256-259)
   first = XNONE;
   const unsigned d0 = s.d;
   if (s.c == FB_UNKNOWN) return s;                             // never observed: distance_ = -10000 is never > tmp (:382)

@@ -34,13 +34,18 @@ enum {
 };
 
 /* Ordering mode of UpdateOccupancy / UpdateESDF.
- *  FAST : order-free parallel wavefront.  Occupancy, counters and queries are bit-exact; distance_ is bit-exact wherever the
- *         reference's result does not depend on its FIFO arrival order (every fully observed scene); exact distance ties keep
- *         the smallest obstacle coordinate instead of the first arrival.
- *  EXACT: reproduces the reference's sequential FIFO order on the device (insert/delete queue order, LIFO dependant lists,
- *         dirs_ order, intra-queue visibility): closest_obstacle_ and distance_ equal the reference bit for bit in every
- *         scene, and the expansion count equals the reference's "Expanding N nodes".  Several times slower than FAST. */
-enum { FIESTA_MODE_FAST = 0, FIESTA_MODE_EXACT = 1 };
+ *  EXACT (the default, = a zero-initialised fiesta_config): reproduces the reference's sequential FIFO order on the device
+ *         (insert/delete queue order, LIFO dependant lists, dirs_ order, intra-queue visibility): closest_obstacle_ and
+ *         distance_ equal the reference bit for bit in every scene, and the expansion count equals the reference's
+ *         "Expanding N nodes".  This is the mode that reproduces the reference.
+ *  FAST : order-free parallel wavefront, several times faster.  Occupancy, counters and queries are bit-exact; distance_ is
+ *         bit-exact wherever the reference's result does not depend on its FIFO arrival order (fully observed scenes with
+ *         sparse obstacles); on partially observed scenes (every ray-cast map) a fraction of a percent to a few percent of
+ *         the distances differ from the reference by up to a few voxels, and exact distance ties keep the smallest obstacle
+ *         coordinate instead of the first arrival.  Opt in explicitly.
+ * The environment variable FIESTA_B200_MODE=exact|fast, when set, overrides fiesta_config.mode in fiesta_create (a knob for
+ * callers that construct the map through the C++ facade without touching its arguments). */
+enum { FIESTA_MODE_EXACT = 0, FIESTA_MODE_FAST = 1 };
 
 /* ESDFMap::ESDFMap(origin, resolution, map_size) arguments (ESDFMap.h:116, ESDFMap.cpp:171-213) plus placement. */
 typedef struct fiesta_config {
@@ -48,7 +53,7 @@ typedef struct fiesta_config {
   double resolution;    /* voxel edge, metres */
   double map_size[3];   /* r_cornor_ - l_cornor_, metres; grid = ceil(map_size / resolution) */
   int32_t device;       /* CUDA device ordinal */
-  int32_t mode;         /* FIESTA_MODE_FAST (0) or FIESTA_MODE_EXACT (1), see below */
+  int32_t mode;         /* FIESTA_MODE_EXACT (0, default) or FIESTA_MODE_FAST (1), see above */
   int32_t reserved[6];  /* must be zero */
 } fiesta_config;
 

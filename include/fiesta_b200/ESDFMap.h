@@ -49,12 +49,16 @@ class ESDFMap {
   int grid_total_size_;   // ESDFMap.h:115, read by Fiesta.h:107-108
 
   // ESDFMap(origin, resolution, map_size) -- ESDFMap.h:116, ESDFMap.cpp:171-213
-  ESDFMap(Eigen::Vector3d origin, double resolution, Eigen::Vector3d map_size, int device = 0)
+  // `mode`: FIESTA_MODE_EXACT (default) reproduces the reference's distance_ / closest_obstacle_ bit for bit;
+  // FIESTA_MODE_FAST is the faster order-free wavefront whose distances differ slightly on ray-cast maps (fiesta_b200.h).
+  // FIESTA_B200_MODE=exact|fast in the environment overrides it without a rebuild.
+  ESDFMap(Eigen::Vector3d origin, double resolution, Eigen::Vector3d map_size, int device = 0, int mode = FIESTA_MODE_EXACT)
       : resolution_(resolution), origin_(origin) {
     fiesta_config cfg = {};
     for (int i = 0; i < 3; ++i) { cfg.origin[i] = origin(i); cfg.map_size[i] = map_size(i); }
     cfg.resolution = resolution;
     cfg.device = device;
+    cfg.mode = mode;
     check(fiesta_create(&cfg, &h_), "fiesta_create");
     grid_total_size_ = fiesta_grid_total_size(h_);
     int gs[3];

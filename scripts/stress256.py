@@ -40,7 +40,7 @@ def main():
     import torch
     import fiesta_b200
     nref = json.load(open(NREF))["frames"] if os.path.exists(NREF) else []
-    m = fiesta_b200.ESDFMap(ORIGIN, RES, SIZE)
+    m = fiesta_b200.ESDFMap(ORIGIN, RES, SIZE, mode="fast")
     m.SetParameters(*scenes.PARAMS_TOGGLE)
     allv = scenes.all_voxels(m.grid_size)
     m.SetOccupancyBatchVox(allv, np.zeros(len(allv), np.uint8)); m.UpdateOccupancy(True); m.UpdateESDF()

@@ -18,11 +18,11 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 origin, res, size = (-3.2, -3.2, -1.6), 0.1, (6.4, 6.4, 3.2)
-m = fiesta_b200.ESDFMap(origin, res, size, device=local)
+m = fiesta_b200.ESDFMap(origin, res, size, device=local, mode="fast")
 m.SetParameters(*scenes.PARAMS_TOGGLE)
 info = m.set_shard(rank, world)
 bufs = shard.HaloBuffers(info.layer_words, torch.device("cuda", local))
-ref = fiesta_b200.ESDFMap(origin, res, size, device=local)      # unsharded FAST map on the same GPU
+ref = fiesta_b200.ESDFMap(origin, res, size, device=local, mode="fast")      # unsharded FAST map on the same GPU
 ref.SetParameters(*scenes.PARAMS_TOGGLE)
 ora = pyoracle.OracleMap(origin, res, size) if rank == 0 else None
 if ora:

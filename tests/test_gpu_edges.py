@@ -108,6 +108,43 @@ def test_local_update_box(oracle_built, mode):
         m.SetOriginalRange()
 
 
+def test_local_map_moving_box_exact(oracle_built):
+    """Local-map mode (Fiesta.h:509-513 with global_update_ = false): a sliding update box + UpdateOccupancy(false).  A voxel
+    observed outside the PREVIOUS box is reset to occupancy 0 / distance +infinity_ while its closest obstacle and its place in
+    that obstacle's dependant list are kept (ESDFMap.cpp:256-259); the order-exact mode reproduces that state and everything
+    that follows from it (arrays compared after every update)."""
+    dev, ora = pair(oracle_built, "exact", params=scenes.PARAMS_TOGGLE)
+    allv = scenes.all_voxels(dev.grid_size)
+    rng = np.random.default_rng(7)
+    idx = rng.choice(len(allv), 300, replace=False)
+    for m in (dev, ora):                                        # every voxel observed, 300 obstacles: finite distances everywhere
+        m.SetOccupancyBatchVox(allv, np.zeros(len(allv), np.uint8)); m.UpdateOccupancy(True); m.UpdateESDF()
+        m.SetOccupancyBatchVox(allv[idx], np.ones(300, np.uint8)); m.UpdateOccupancy(True); m.UpdateESDF()
+        m.SetParameters(*scenes.PARAMS_DEFAULT)                 # from here on one miss no longer clamps: resets are not skipped (:250-255)
+    seen_reset = 0
+    for r in range(8):
+        c = np.array([-1.2 + 0.35 * r, -0.9 + 0.3 * r, 0.0])                       # the box slides through the map
+        lo, hi = c - np.array([1.3, 1.2, 0.9]), c + np.array([1.3, 1.2, 0.9])
+        for m in (dev, ora):
+            m.SetUpdateRange(lo, hi)
+        vox = np.stack([rng.integers(0, dev.grid_size[i], 6000) for i in range(3)], -1).astype(np.int32)
+        occ = (rng.random(6000) < 0.4).astype(np.uint8)
+        assert np.array_equal(dev.SetOccupancyBatchVox(vox, occ), ora.SetOccupancyBatchVox(vox, occ))
+        assert dev.UpdateOccupancy(False) == ora.UpdateOccupancy(False)
+        res = compare(dev, ora)
+        assert res["occ"] == 0 and res["dist"] == 0 and res["cobs_tie"] == 0 and res["cobs_nontie"] == 0, ("after UpdateOccupancy", r, res)
+        dev.UpdateESDF(); ora.UpdateESDF()
+        res = compare(dev, ora)
+        assert res["occ"] == 0 and res["dist"] == 0 and res["cobs_tie"] == 0 and res["cobs_nontie"] == 0, (r, res)
+        assert dev.stats()["expansions"] == ora.stats()["expansions"], r
+        D = ora.export_distance(); C = ora.export_closest_obstacle()
+        seen_reset += int(((D == 10000) & (C[:, 0] != -10000)).sum())          # "distance infinity, obstacle kept" states persist
+    assert seen_reset > 0
+    q = rng.uniform(-2.5, 2.5, (256, 3)) * (1, 1, 0.5)
+    d1, g1 = dev.GetDistWithGradTrilinearBatch(q); d2, g2 = ora.GetDistWithGradTrilinearBatch(q)
+    assert np.array_equal(d1, d2) and np.array_equal(g1, g2)
+
+
 def test_device_resident_event_batch(oracle_built):
     """fiesta_set_occupancy_batch_vox_device == the host SetOccupancy loop (events already in HBM; dynamic-obstacle stress path)."""
     import torch

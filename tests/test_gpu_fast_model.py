@@ -38,7 +38,7 @@ def test_insert_delete_replay_equals_model(oracle_built, G, res, observed):
     rng = np.random.default_rng(5)
     params = scenes.PARAMS_TOGGLE
     size = ((G - 0.5) * res,) * 3
-    dev = fiesta_b200.ESDFMap((-1.0, -2.0, 0.5), res, size)
+    dev = fiesta_b200.ESDFMap((-1.0, -2.0, 0.5), res, size, mode="fast")
     dev.SetParameters(*params)
     model = oracle_built.FastModel(dev.grid_size, res, logit(params[4]))
     gs = dev.grid_size
@@ -62,7 +62,7 @@ def test_lidar_frames_equal_model(oracle_built):
     import fiesta_b200
     params = scenes.PARAMS_DEFAULT
     origin, res, size = (-3.2, -3.2, -3.2), 0.05, (6.4, 6.4, 6.4)
-    dev = fiesta_b200.ESDFMap(origin, res, size)
+    dev = fiesta_b200.ESDFMap(origin, res, size, mode="fast")
     dev.SetParameters(*params)
     model = oracle_built.FastModel(dev.grid_size, res, logit(params[4]))
     sc = scenes.Scene((3.0, 3.0, 1.5), 14, 5, seed=21)

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 def make_pair(oracle_built, origin, res, size, params):
     import fiesta_b200
-    dev = fiesta_b200.ESDFMap(origin, res, size)
+    dev = fiesta_b200.ESDFMap(origin, res, size, mode="fast")
     ora = oracle_built.OracleMap(origin, res, size)
     dev.SetParameters(*params)
     ora.SetParameters(*params)
