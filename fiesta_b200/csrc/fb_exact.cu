@@ -130,9 +130,9 @@ __global__ void k_x_gather64(const unsigned long long *src, const uint32_t *idx,
 __global__ void k_x_gather32(const uint32_t *src, const uint32_t *idx, unsigned n, uint32_t *dst) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) dst[i] = src[idx[i]];
 }
-__global__ void k_x_set_ord(const uint32_t *deps, unsigned n, uint32_t *ord, uint32_t *nc) {
+__global__ void k_x_set_ord(const uint32_t *deps, unsigned n, uint32_t *ord, uint32_t *nc, uint8_t *nk) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { ord[deps[i]] = i; nc[i] = FB_INF; }
+  if (i < n) { ord[deps[i]] = i; nc[i] = FB_INF; nk[i] = 24; }
 }
 __global__ void k_x_fill32(uint32_t *a, size_t n, uint32_t val) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] = val;
@@ -321,7 +321,8 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
         if ((e = x_sort_pairs(X, X->k1b, X->k2b, X->idx[1], X->idx[0], ndep, s))) return e;
         k_x_gather32<<<nblk(ndep), 256, 0, s>>>(X->dv, X->idx[0], ndep, X->deps);
         k_x_fill32<<<148 * 8, 256, 0, s>>>(scratch, P, XNONE);
-        k_x_set_ord<<<nblk(ndep), 256, 0, s>>>(X->deps, ndep, scratch, X->nc[0]);
+        if ((e = x_ensure(X, &X->flags2, &X->cap_flags2, ndep))) return e;
+        k_x_set_ord<<<nblk(ndep), 256, 0, s>>>(X->deps, ndep, scratch, X->nc[0], X->flags2);
         *launches += 8;
         ndep_run = ndep; ls_deps = X->tclock;                // the fixpoint and the hand-over to E[0] run inside k_x_relax
         X->tclock += ndep;
@@ -341,7 +342,7 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
     memset(h, 0, sizeof(*h));
     h->gen_id = X->gen_id; h->wclock = X->wclock; h->tclock = X->tclock; h->sclock = X->sclock;
     XCK(cudaMemcpyAsync(X->d_ctl, h, sizeof(FbXCtl), cudaMemcpyHostToDevice, s));
-    XCK(fb_xrelax_launch(X, g, cobs, nE, X->deps, ndep_run, scratch, X->nc[0], occbits, ls_deps, xdbg ? X->d_dbg : nullptr, s));
+    XCK(fb_xrelax_launch(X, g, cobs, nE, X->deps, ndep_run, scratch, X->nc[0], X->flags2, occbits, ls_deps, xdbg ? X->d_dbg : nullptr, s));
     XCK(cudaMemcpyAsync(h, X->d_ctl, sizeof(FbXCtl), cudaMemcpyDeviceToHost, s));
     XCK(cudaStreamSynchronize(s));
     *launches += 1;

@@ -62,5 +62,5 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
 // fb_xrelax.cu
 cudaError_t fb_xrelax_init();
 int fb_xrelax_blocks(int device);
-cudaError_t fb_xrelax_launch(FbExact *X, const FbGeom &g, uint32_t *cobs, unsigned nE0, const uint32_t *deps, unsigned ndep, uint32_t *ord, uint32_t *nc,
+cudaError_t fb_xrelax_launch(FbExact *X, const FbGeom &g, uint32_t *cobs, unsigned nE0, const uint32_t *deps, unsigned ndep, uint32_t *ord, uint32_t *nc, uint8_t *nk,
                              const uint32_t *occbits, unsigned long long ls_deps, unsigned long long *dbg, cudaStream_t s);

@@ -179,6 +179,7 @@ struct XArgs {
   const uint32_t *deps; unsigned ndep;
   uint32_t *ord;            // per voxel: position in deps, or XNONE
   uint32_t *nc;             // per dependant: re-seeded code (FB_INF at start)
+  uint8_t *nk;              // per dependant: direction of the neighbour the code was taken from (24 = none)
   const uint32_t *occbits;
   unsigned long long ls_deps;   // link time of dependant 0 (InsertIntoList order, :333)
   unsigned long long *dbg;  // optional per-generation trace {nE, rounds, ns} (FIESTA_DEBUG_X)
@@ -195,6 +196,36 @@ __device__ __forceinline__ void x_claim_summaries(const XArgs &a, const XShared 
   if (!fb_in_grid(a.g, nx, ny, nz) || !(lane == 24u || fb_in_range(a.g, nx, ny, nz))) return;
   const long long n = fb_ii(a.g, nx, ny, nz);
   if (__ldcg(&a.SUMg[n]) != sclock && atomicExch(&a.SUMg[n], sclock) != sclock) x_summarize(a.g, a.cobs, a.MB, a.SUM, nx, ny, nz);
+}
+
+// After element i (at x,y,z) flipped: bring the summaries of its <= 25 targets up to date (one warp; lane k = target k).
+// The offer of (i, k) carries the timestamp 32*i + k whatever its code, so a summary has to be recomputed only if that
+// timestamp is its `first` or `best` (the old offer defined it) or if the element's new offer would become one of them;
+// otherwise neither removing the old offer nor adding the new one changes {first, best}.
+__device__ __forceinline__ void x_refresh_summaries(const XArgs &a, const XShared &sh, unsigned lane, unsigned i, uint32_t p, int x, int y, int z) {
+  unsigned long long w = 0;
+  if (lane == 0) w = __ldcg(&a.MB[p]);
+  w = __shfl_sync(0xffffffffu, w, 0);
+  if (lane >= 25u) return;
+  int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
+  const int nx = x + dx, ny = y + dy, nz = z + dz;
+  if (!fb_in_grid(a.g, nx, ny, nz) || !(lane == 24u || fb_in_range(a.g, nx, ny, nz))) return;
+  const uint4 u = __ldcg(&a.SUM[fb_ii(a.g, nx, ny, nz)]);
+  if (u.w == FB_UNKNOWN) return;                               // never observed: accepts nothing, its summary never changes
+  const unsigned ts = i * 32u + lane;
+  bool redo = u.x == ts || u.y == ts;
+  if (!redo) {
+    const unsigned long long kind = x_mb_kind(w);
+    const uint32_t c = x_mb_code(w);
+    if (((kind == X_PUSH && lane < 24u) || (kind == X_PULL && lane == 24u)) && c >= 2u) {
+      // the snapshot distance is not in the summary (a voxel whose distance was forced to infinity keeps its code): an offer
+      // that does not beat the current best cannot matter, one that does is checked against the snapshot by the recomputation
+      const unsigned d = x_d2(nx, ny, nz, c);
+      if (u.y == XNONE) redo = true;                           // no accepted offer so far: the new one may be the first
+      else { const unsigned bd = x_d2(nx, ny, nz, u.z); redo = ts < u.x || d < bd || (d == bd && ts < u.y); }
+    }
+  }
+  if (redo) x_summarize(a.g, a.cobs, a.MB, a.SUM, nx, ny, nz);
 }
 
 // Behaviour of element i (one warp; lanes 0..23 = neighbour k at pop time, lane 24 = the element itself).  Returns the new word.
@@ -245,8 +276,9 @@ __device__ __forceinline__ unsigned x_block_scan(XShared &sh, unsigned c, unsign
 
 // One evaluation of the re-seeding rule: dependant i takes the closest obstacle of the FIRST neighbour in dirs_ order that
 // has a valid one (:308-321); dependants processed earlier expose their new value, later ones their (deleted) old one.
-__device__ __forceinline__ uint32_t x_reseed_eval(const XArgs &a, unsigned i, int x, int y, int z) {
+__device__ __forceinline__ uint32_t x_reseed_eval(const XArgs &a, unsigned i, int x, int y, int z, unsigned &kc) {
   const FbGeom &g = a.g;
+  kc = 24u;
   for (int k = 0; k < 24; ++k) {
     const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
     if (!fb_in_range(g, nx, ny, nz) || !fb_in_grid(g, nx, ny, nz)) continue;
@@ -258,7 +290,7 @@ __device__ __forceinline__ uint32_t x_reseed_eval(const XArgs &a, unsigned i, in
     if (c >= 2u) {
       int ox, oy, oz; fb_unpack(c, ox, oy, oz);
       const long long oi = fb_ii(g, ox, oy, oz);
-      if ((__ldg(&a.occbits[oi >> 5]) >> (oi & 31)) & 1u) return c;   // Exist(closest obstacle) (:312), then `break` (:319)
+      if ((__ldg(&a.occbits[oi >> 5]) >> (oi & 31)) & 1u) { kc = (unsigned)k; return c; }   // Exist(closest obstacle) (:312), then `break` (:319)
     }
   }
   return FB_INF;
@@ -301,14 +333,29 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
       for (unsigned q = gtid; q < nw; q += gthreads) {
         const unsigned i = r == 1u ? q : __ldcg(&a.W[in][q]);
         int x, y, z; x_coords(g, __ldcg(&a.deps[i]), x, y, z);
-        const uint32_t res = x_reseed_eval(a, i, x, y, z);
-        if (res == __ldcg(&a.nc[i])) continue;
+        unsigned kc;
+        const uint32_t res = x_reseed_eval(a, i, x, y, z, kc);
+        const uint32_t was = __ldcg(&a.nc[i]);
+        a.nk[i] = (uint8_t)kc;
+        if (res == was) continue;
         a.nc[i] = res;
         for (int k = 0; k < 24; ++k) {                         // later dependants that look at this one
           const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
           if (!fb_in_grid(g, nx, ny, nz)) continue;
           const unsigned o = __ldcg(&a.ord[fb_ii(g, nx, ny, nz)]);
-          const bool push = o != XNONE && o > i && __ldcg(&a.wstamp[o]) != wclock && atomicExch(&a.wstamp[o], wclock) != wclock;
+          bool push = o != XNONE && o > i;
+          if (push) {
+            const unsigned so = __ldcg(&a.wstamp[o]);
+            push = so != wclock;                               // not listed for the next round yet
+            // A dependant that is NOT being evaluated in this round holds a stable choice: it looks at this voxel through
+            // direction k^1 and only cares if that direction comes before its current source (and this one became valid) or
+            // is its current source.  One that is being evaluated right now may have missed the new value: always listed.
+            if (push && r > 1u && so != wclock - 1u) {
+              const unsigned ko = __ldcg(&a.nk[o]), kd = (unsigned)k ^ 1u;
+              push = kd == ko || (kd < ko && res >= 2u);
+            }
+            push = push && atomicExch(&a.wstamp[o], wclock) != wclock;
+          }
           const unsigned slot2 = fb_warp_append(&ctl->nW[out], push);
           if (push) a.W[out][slot2] = o;
         }
@@ -390,12 +437,10 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
         ++dense_total;
         if (nf < nE / 4u) {                                    // few flips: only the targets of last round's flips
           for (unsigned q = gwarp; q < nf; q += gwarps) {
-            int x, y, z; x_coords(g, __ldcg(&E[__ldcg(&a.F[in][q])]), x, y, z);
-            if (lane < 25) {
-              int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
-              const int nx = x + dx, ny = y + dy, nz = z + dz;
-              if (fb_in_grid(g, nx, ny, nz) && (lane == 24 || fb_in_range(g, nx, ny, nz))) x_summarize(g, a.cobs, a.MB, a.SUM, nx, ny, nz);
-            }
+            const unsigned i = __ldcg(&a.F[in][q]);
+            const uint32_t p = __ldcg(&E[i]);
+            int x, y, z; x_coords(g, p, x, y, z);
+            x_refresh_summaries(a, sh, lane, i, p, x, y, z);
           }
         } else {
           ++sclock;
@@ -409,12 +454,9 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
       for (unsigned q = gwarp; q < nw + nref; q += gwarps) {
         if (q >= nw) {                                         // summaries of the targets of an element that flipped last round
           const unsigned i = __ldcg(&a.F[in][q - nw]);
-          int x, y, z; x_coords(g, __ldcg(&E[i]), x, y, z);
-          if (lane < 25) {
-            int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
-            const int nx = x + dx, ny = y + dy, nz = z + dz;
-            if (fb_in_grid(g, nx, ny, nz) && (lane == 24 || fb_in_range(g, nx, ny, nz))) x_summarize(g, a.cobs, a.MB, a.SUM, nx, ny, nz);
-          }
+          const uint32_t p = __ldcg(&E[i]);
+          int x, y, z; x_coords(g, p, x, y, z);
+          x_refresh_summaries(a, sh, lane, i, p, x, y, z);
           continue;
         }
         const unsigned i = r == 1u ? q : __ldcg(&wl[q]);
@@ -580,10 +622,10 @@ int fb_xrelax_blocks(int device) {
   return sms;                                                  // one CTA per SM: the barrier is cheapest with few arrivals
 }
 
-cudaError_t fb_xrelax_launch(FbExact *X, const FbGeom &g, uint32_t *cobs, unsigned nE0, const uint32_t *deps, unsigned ndep, uint32_t *ord, uint32_t *nc,
+cudaError_t fb_xrelax_launch(FbExact *X, const FbGeom &g, uint32_t *cobs, unsigned nE0, const uint32_t *deps, unsigned ndep, uint32_t *ord, uint32_t *nc, uint8_t *nk,
                              const uint32_t *occbits, unsigned long long ls_deps, unsigned long long *dbg, cudaStream_t s) {
   XArgs a;
-  a.deps = deps; a.ndep = ndep; a.ord = ord; a.nc = nc; a.occbits = occbits; a.ls_deps = ls_deps;
+  a.deps = deps; a.ndep = ndep; a.ord = ord; a.nc = nc; a.nk = nk; a.occbits = occbits; a.ls_deps = ls_deps;
   a.g = g; a.cobs = cobs; a.MB = X->MB; a.LS = X->LS; a.SUM = X->SUM; a.SUMg = X->SUMg;
   a.E[0] = X->E[0]; a.E[1] = X->E[1]; a.emask = X->emask;
   for (int k = 0; k < 3; ++k) { a.W[k] = X->W[k]; a.F[k] = X->F[k]; }

@@ -102,8 +102,15 @@ static u32 sclock=0;
 static void claim_summaries(long i){ long p=E[cur][i]; int x,y,z; vxyz(p,&x,&y,&z);
   for(int k=0;k<25;k++){ int nx=k<24?x+DIRS[k][0]:x,ny=k<24?y+DIRS[k][1]:y,nz=k<24?z+DIRS[k][2]:z; if(!ing(nx,ny,nz)||(k<24&&!inb(nx,ny,nz))) continue;
     long n=vi(nx,ny,nz); if(SUMg[n]!=sclock){ SUMg[n]=sclock; summarize(nx,ny,nz); } } }
-static void refresh_targets(long i){ long p=E[cur][i]; int x,y,z; vxyz(p,&x,&y,&z);
-  for(int k=0;k<25;k++){ int nx=k<24?x+DIRS[k][0]:x,ny=k<24?y+DIRS[k][1]:y,nz=k<24?z+DIRS[k][2]:z; if(!ing(nx,ny,nz)||(k<24&&!inb(nx,ny,nz))) continue; summarize(nx,ny,nz); } }
+// after element i flipped: its offer (i,k) carries timestamp 32i+k whatever its code, so the summary of target k changes only if
+// that timestamp is its `first` / `best`, or if the element's new offer would become one of them
+static void refresh_targets(long i){ long p=E[cur][i]; int x,y,z; vxyz(p,&x,&y,&z); u64 w=MB[p];
+  for(int k=0;k<25;k++){ int nx=k<24?x+DIRS[k][0]:x,ny=k<24?y+DIRS[k][1]:y,nz=k<24?z+DIRS[k][2]:z; if(!ing(nx,ny,nz)||(k<24&&!inb(nx,ny,nz))) continue;
+    sum_t u=SUM[vi(nx,ny,nz)]; if(u.snap_c==CU) continue; u32 ts=(u32)i*32+k; int redo=u.first==ts||u.best_ts==ts;
+    if(!redo){ u64 kind=mb_kind(w); u32 c=mb_code(w);
+      if(((kind==K_PUSH&&k<24)||(kind==K_PULL&&k==24))&&c>=2){ u32 d=d2(nx,ny,nz,c);
+        if(u.best_ts==NONE) redo=1; else { u32 bd=d2(nx,ny,nz,u.best_c); redo=ts<u.first||d<bd||(d==bd&&ts<u.best_ts); } } }
+    if(redo) summarize(nx,ny,nz); } }
 static void relax(void){
   int big=nE>SMALL;
   for(long i=0;i<nE;i++) MB[E[cur][i]]=mbw((u32)i,K_PUSH,C[E[cur][i]]);   // initial guess: everybody pushes its snapshot code

@@ -9,9 +9,9 @@ w = bench.WORKLOADS[wl]
 frames = bench.make_frames(wl, nfr)
 m = fiesta_b200.ESDFMap(w['origin'], w['res'], w['size'], device=0, mode='exact')
 m.SetParameters(*scenes.PARAMS_DEFAULT)
-for f, (pts, T) in enumerate(frames):
+for f, fr in enumerate(frames):
     t0 = time.perf_counter()
-    m.RaycastFrame(pts, T, w['min_len'], w['max_len'])
+    m.RaycastFrame(fr['pts'], fr['T'], w['min_len'], w['max_len'])
     if m.CheckUpdate():
         m.SetOriginalRange(); m.UpdateOccupancy(True); m.UpdateESDF()
     s = m.stats()
