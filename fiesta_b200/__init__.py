@@ -63,6 +63,8 @@ SYMBOLS = [
     "fiesta_get_dist_grad_trilinear", "fiesta_get_distance_batch_pos", "fiesta_get_dist_grad_trilinear_batch",
     "fiesta_export_distance", "fiesta_export_closest_obstacle", "fiesta_export_occupancy", "fiesta_export_counters",
     "fiesta_get_stats", "fiesta_synchronize", "fiesta_set_shard", "fiesta_shard_pack", "fiesta_shard_ingest", "fiesta_shard_relax", "fiesta_get_point_cloud", "fiesta_get_slice_marker", "fiesta_set_occupancy_batch_vox_device", "fiesta_depth_frame", "fiesta_last_depth_cloud",
+    "fiesta_query_plan_create", "fiesta_query_plan_destroy", "fiesta_query_plan_positions", "fiesta_query_plan_distances",
+    "fiesta_query_plan_gradients", "fiesta_query_plan_run",
 ]
 
 _lib = None
@@ -86,12 +88,43 @@ def load_library():
         L.fiesta_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
         L.fiesta_destroy.argtypes = [C.c_void_p]
         L.fiesta_destroy.restype = None
+        L.fiesta_query_plan_create.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+        L.fiesta_query_plan_destroy.argtypes = [C.c_void_p]
+        L.fiesta_query_plan_destroy.restype = None
+        L.fiesta_query_plan_run.argtypes = [C.c_void_p]
+        for n in ("fiesta_query_plan_positions", "fiesta_query_plan_distances", "fiesta_query_plan_gradients"):
+            getattr(L, n).argtypes = [C.c_void_p]
+            getattr(L, n).restype = C.POINTER(C.c_double)
         _lib = L
     return _lib
 
 
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class QueryPlan:
+    """fiesta_query_plan: positions in, distances + gradients out, one graph launch per run()."""
+
+    def __init__(self, m, n):
+        self._m, self.n = m, int(n)
+        h = C.c_void_p()
+        m._ck(m._L.fiesta_query_plan_create(m._h, self.n, C.byref(h)), "fiesta_query_plan_create")
+        self._h = h
+        self.positions = np.ctypeslib.as_array(m._L.fiesta_query_plan_positions(h), shape=(self.n, 3))
+        self.distances = np.ctypeslib.as_array(m._L.fiesta_query_plan_distances(h), shape=(self.n,))
+        self.gradients = np.ctypeslib.as_array(m._L.fiesta_query_plan_gradients(h), shape=(self.n, 3))
+
+    def run(self, pos=None):
+        if pos is not None:
+            self.positions[:] = pos
+        self._m._ck(self._m._L.fiesta_query_plan_run(self._h), "fiesta_query_plan_run")
+        return self.distances, self.gradients
+
+    def close(self):
+        if self._h:
+            self._m._L.fiesta_query_plan_destroy(self._h)
+            self._h = None
 
 
 class ESDFMap:
@@ -211,6 +244,10 @@ class ESDFMap:
         return d, g
 
     # --- Fiesta::RaycastMultithread (Fiesta.h:281-303), serial semantics ---
+    def QueryPlan(self, n):
+        """Fixed-size GetDistWithGradTrilinear batch as a CUDA graph over pinned buffers (fiesta_query_plan_*)."""
+        return QueryPlan(self, n)
+
     def RaycastFrame(self, xyz, T, min_ray_length, max_ray_length):
         """xyz: (n,3) float32 host array, or an integer device pointer paired with `n` as a tuple (ptr, n)."""
         p = RaycastParams(float(min_ray_length), float(max_ray_length))

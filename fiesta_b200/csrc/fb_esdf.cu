@@ -25,7 +25,6 @@
 #include <cooperative_groups.h>
 #include <stdio.h>
 #include "fb_common.cuh"
-#include "fb_exit_test.h"
 
 namespace cg = cooperative_groups;
 
@@ -125,10 +124,6 @@ __device__ __forceinline__ void tma_load_box(void *dst, const CUtensorMap *tmap,
 #ifndef WF_GROUP
 #define WF_GROUP 2          // lanes that share the evaluation of one listed voxel (1, 2, 4 or 8)
 #endif
-#ifndef WF_EXIT_TEST
-#define WF_EXIT_TEST 0        // 1: a visiting tile checks whether its changes can improve a neighbour's border before queueing it
-                              // (experimental, DESIGN.md section 8: halves the visits; validate with tests/test_gpu_fast_model.py)
-#endif
 #ifndef WF_CTAS
 #define WF_CTAS 4           // resident CTAs per SM the register budget is sized for
 #endif
@@ -148,12 +143,6 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
   __shared__ uint32_t listF[FB_TILE * FB_TILE * FB_TILE], res[FB_TILE * FB_TILE * FB_TILE];
   __shared__ unsigned s_cnt[2];
   __shared__ int s_koff[24];
-#if WF_EXIT_TEST
-  // per z-row: records changed by this visit, in a 16x16 row array with a 2-row zero border (index (rx+2)*16 + (ry+2)) so
-  // that the 13 neighbour rows of any box row can be read without bounds checks; only interior rows are ever written
-  __shared__ uint32_t cmp[16 * 16];
-  __shared__ unsigned s_need;                // neighbour directions ((ox+1)*9 + (oy+1)*3 + (oz+1)) whose border would improve
-#endif
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   const int ly = (tid >> 3) & 7, lz = tid & 7;
@@ -165,14 +154,15 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
   }
   // dirs_ (parameters.h:55-68) grouped by z-row so that the queue bits of all 24 neighbours come out of 13 mask words:
   // same row dz = -2,-1,+1,+2 | rows x-1, x+1, y-1, y+1 with dz = -1,0,+1 | the four xy diagonals | x-2, x+2, y-2, y+2
-  constexpr int kd[24][3] = FBX_KD_INIT;
+  constexpr int kd[24][3] = {{0, 0, -2}, {0, 0, -1}, {0, 0, 1}, {0, 0, 2},
+                             {-1, 0, -1}, {-1, 0, 0}, {-1, 0, 1}, {1, 0, -1}, {1, 0, 0}, {1, 0, 1},
+                             {0, -1, -1}, {0, -1, 0}, {0, -1, 1}, {0, 1, -1}, {0, 1, 0}, {0, 1, 1},
+                             {-1, -1, 0}, {-1, 1, 0}, {1, -1, 0}, {1, 1, 0},
+                             {-2, 0, 0}, {2, 0, 0}, {0, -2, 0}, {0, 2, 0}};
 #pragma unroll
   for (int k = 0; k < 24; ++k)
     if (tid == k) s_koff[k] = kd[k][0] * (FB_BOX * FB_BOXZ) + kd[k][1] * FB_BOXZ + kd[k][2];
 
-#if WF_EXIT_TEST
-  cmp[tid] = 0u;                              // WF_THREADS == 256 == 16 * 16
-#endif
   if (tid < FB_BOX * FB_BOX) {
     const int rx = tid / FB_BOX, ry = tid % FB_BOX;
     const bool inner = rx >= FB_HALO && rx < FB_HALO + FB_TILE && ry >= FB_HALO && ry < FB_HALO + FB_TILE;
@@ -398,17 +388,7 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
           atomicMin(&s_bbox[4], lz); atomicMax(&s_bbox[5], lz);
         }
         diff = diff || outw[h] != orig[h];
-#if WF_EXIT_TEST
-        {
-          const uint32_t bc = __ballot_sync(0xffffffffu, changed);
-          const int lane = tid & 31;
-          if (lane < 4) cmp[(lxh[h] + FB_HALO + 2) * 16 + (((tid >> 5) & 1) * 4 + lane + FB_HALO + 2)] = ((bc >> (8 * lane)) & 0xffu) << FB_ZPAD;
-        }
-#endif
       }
-#if WF_EXIT_TEST
-      if (tid == 0) { s_need = 0u; s_cnt[0] = 0u; }
-#endif
       const int nchanged = __syncthreads_count(nch > 0) ;      // threads with a change (exact voxel count accumulated below)
       const int dirty = __syncthreads_or(diff);               // also true when only stale FRESH flags must be retired
       if (dirty) {
@@ -422,70 +402,6 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
         const unsigned c2 = __reduce_add_sync(0xffffffffu, (unsigned)nch);     // exact number of changed voxels, per warp
         if ((tid & 31) == 0 && c2) atomicAdd(&a.ctr->voxels_changed, (unsigned long long)c2);
       }
-#if WF_EXIT_TEST
-      // Exit test.  Next generation only the records changed here are in the queue; the halo of this box holds the
-      // neighbours' current border values, records only improve, and a neighbour voxel that is queued itself gets its tile
-      // visited anyway.  So a neighbour has to be queued for the sake of THIS tile iff one of its border voxels would take
-      // a candidate from one of the changed records -- decided here exactly, one thread per z-row of the box.
-      unsigned need27 = 0;
-      if (nchanged) {
-        // (X1) one thread per z-row of the box lists the halo voxels that have a changed record among their 24 neighbours
-        if (tid < FB_BOX * FB_BOX) {
-          uint32_t act = fbx_row_candidates(cmp, tid / FB_BOX, tid % FB_BOX);
-          if (act) {
-            const unsigned cnt = (unsigned)__popc(act);
-            unsigned pos = atomicAdd(&s_cnt[0], cnt);
-            if (pos + cnt > (unsigned)(FB_TILE * FB_TILE * FB_TILE)) atomicOr(&s_need, 0x07ffffffu);   // list full: queue as the box rule says
-            else
-              while (act) {
-                const int zb = __ffs(act) - 1;
-                act &= act - 1u;
-                listV[pos++] = (unsigned short)((tid << 4) | zb);
-              }
-          }
-        }
-        __syncthreads();
-        // (X2) the listed voxels are checked like step (B): WF_GROUP lanes each, only against the changed neighbours
-        {
-          constexpr int GE = 32 / WF_GROUP;
-          constexpr uint32_t slice0 = WF_GROUP == 1 ? 0xffffffu : WF_GROUP == 2 ? 0x555555u : WF_GROUP == 4 ? 0x111111u : 0x010101u;
-          const int lane = tid & 31, sub = lane % WF_GROUP;
-          const int n = s_cnt[0] > (unsigned)(FB_TILE * FB_TILE * FB_TILE) ? 0 : (int)s_cnt[0];   // (overflow: every direction is already asked for)
-          for (int e0 = (tid >> 5) * GE; e0 < n; e0 += (WF_THREADS / 32) * GE) {
-            const int e = e0 + lane / WF_GROUP;
-            if (e >= n) continue;
-            const int v = listV[e];
-            const int row = v >> 4, zb = v & 15, rx = row / FB_BOX, ry = row % FB_BOX;
-            const uint32_t cy = V[row * FB_BOXZ + zb] & FB_CODE_MASK;
-            const int x = x0 - FB_HALO + rx, y = y0 - FB_HALO + ry, z = z0 - FB_ZPAD + zb;
-            if (cy == FB_UNKNOWN || !fb_in_range(g, x, y, z)) continue;      // barrier / outside the box (outside the grid: zero fill)
-            const uint32_t m = fbx_changed_neighbours(cmp, rx, ry, zb) & (slice0 << sub);
-            if (m && fbx_improves(V, s_koff, rx, ry, zb, x, y, z, cy, m)) atomicOr(&s_need, 1u << fbx_dir_bit(rx, ry, zb));
-          }
-        }
-        __syncthreads();
-        if (tid < 32) {                                        // the bounding-box rule stays a necessary condition
-          bool ok = false;
-          if (tid < 27) {
-            const int ox = tid / 9 - 1, oy = (tid / 3) % 3 - 1, oz = tid % 3 - 1;
-            const int nz = (ox != 0) + (oy != 0) + (oz != 0);
-            ok = (nz == 1 || nz == 2) && ((s_need >> tid) & 1u);
-            if (ox < 0) ok = ok && (s_bbox[0] < 2);
-            if (ox > 0) ok = ok && (s_bbox[1] > 5);
-            if (oy < 0) ok = ok && (s_bbox[2] < 2);
-            if (oy > 0) ok = ok && (s_bbox[3] > 5);
-            if (oz < 0) ok = ok && (s_bbox[4] < 2);
-            if (oz > 0) ok = ok && (s_bbox[5] > 5);
-          }
-          need27 = __ballot_sync(0xffffffffu, ok);
-        }
-      }
-      if (tid == 0 && dirty) {
-        const unsigned sl = atomicAdd(&a.ctr->n_changed[par], 1u);
-        a.changed[par][sl] = tile;
-        a.changed_bbox[par][sl] = nchanged ? (need27 | (1u << 31)) : 0u;   // {directions to queue : 27 | some record changed : bit 31}
-      }
-#else
       if (tid == 0 && dirty) {
         const unsigned sl = atomicAdd(&a.ctr->n_changed[par], 1u);
         a.changed[par][sl] = tile;
@@ -493,7 +409,6 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
                                               ((unsigned)s_bbox[3] << 9) | ((unsigned)s_bbox[4] << 12) | ((unsigned)s_bbox[5] << 15) | (1u << 18))
                                            : 0u;
       }
-#endif
       // generic-proxy accesses to buf[slot] must be ordered before the async-proxy (TMA) write of a later prefetch into it
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
@@ -522,18 +437,6 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
           a.cobs[ii] = __ldcg(&a.cobs_b[ii]);
         }
       }
-#if WF_EXIT_TEST
-      if (tid < 27 && (bb >> 31)) {                            // some record changed: queue what the exit test asked for
-        const int ox = tid / 9 - 1, oy = (tid / 3) % 3 - 1, oz = tid % 3 - 1;
-        if (tid == 13) fb_activate(a, tile, stamp, (int)(cur ^ 1u), false);   // revisit once more, only to retire the FRESH flags
-        else if ((bb >> tid) & 1u) {
-          const int nx = txc + ox, ny = tyc + oy, nzc = tzc + oz;
-          if (nx >= 0 && nx < g.tx && ny >= 0 && ny < g.ty && nzc >= 0 && nzc < g.tz)
-            fb_activate(a, (unsigned)((nx * g.ty + ny) * g.tz + nzc), stamp, (int)(cur ^ 1u), true, (unsigned)(g.ty * g.tz));
-        }
-      }
-    }
-#else
       if (tid < 27 && (bb >> 18)) {                            // some record changed: its new value must reach the neighbours
         const int ox = tid / 9 - 1, oy = (tid / 3) % 3 - 1, oz = tid % 3 - 1;
         const int nz = (ox != 0) + (oy != 0) + (oz != 0);
@@ -550,7 +453,6 @@ k_wavefront(const __grid_constant__ CUtensorMap tmap, FbGeom g, FbEsdfArgs a) {
         }
       }
     }
-#endif
     grid.sync();
     if (a.dbg && blockIdx.x == 0 && tid == 0 && gen < 256u) {
       unsigned long long t_c; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_c));

@@ -195,6 +195,8 @@ cudaError_t fb_exact_init(FbExact *X, const FbGeom &g, int device, cudaStream_t 
   XCK(cudaMalloc((void **)&X->wstamp, P * 4)); XCK(cudaMemsetAsync(X->wstamp, 0, P * 4, s));
   for (int k = 0; k < 3; ++k) { XCK(cudaMalloc((void **)&X->W[k], P * 4)); XCK(cudaMalloc((void **)&X->F[k], P * 4)); }
   for (int k = 0; k < 2; ++k) { XCK(cudaMalloc((void **)&X->E[k], P * 4)); X->cap_E[k] = P; }
+  X->dense_min = 4096u;
+  if (const char *e = getenv("FIESTA_X_DENSE")) { long v = atol(e); if (v >= 0 && v <= (1 << 24)) X->dense_min = (unsigned)v; }
   X->small_max = FB_X_SMALL_DEFAULT;
   if (const char *e = getenv("FIESTA_X_SMALL")) { long v = atol(e); if (v >= 0 && v <= 65536) X->small_max = (unsigned)v; }
   XCK(cudaMalloc((void **)&X->slotc, ((size_t)X->small_max + 1) * 32 * 4));
@@ -353,9 +355,9 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
     if (xdbg) {
       static unsigned long long hd[FB_X_DBG_WORDS];
       XCK(cudaMemcpy(hd, X->d_dbg, sizeof(hd), cudaMemcpyDeviceToHost));
-      static const char *cat[12] = {"S", "round1", "rounds", "dense", "commit", "apply", "s.round1", "s.rounds", "s.commit", "s.apply", "top", "empty-barrier(cycles)"};
+      static const char *cat[14] = {"S", "round1", "rounds", "dense", "commit", "apply", "s.round1", "s.rounds", "s.commit", "s.apply", "top", "empty-barrier", "reseed.rounds", "reseed.assemble"};
       fprintf(stderr, "[x] reseed rounds %u; phases (us, count):", st->reseed_rounds);
-      for (int c = 0; c < 12; ++c) fprintf(stderr, " %s %.0f/%llu", cat[c], hd[3 * 1024 + 2 * c] / 1965.0, hd[3 * 1024 + 2 * c + 1]);
+      for (int c = 0; c < 14; ++c) fprintf(stderr, " %s %.0f/%llu", cat[c], hd[3 * 1024 + 2 * c] / 1965.0, hd[3 * 1024 + 2 * c + 1]);
       fprintf(stderr, "\n");
       for (int gq = 0; gq < 2; ++gq) { fprintf(stderr, "[x] gen %d work lists:", gq); for (int r = 0; r < 512 && hd[3 * 1024 + 32 + gq * 512 + r]; ++r) fprintf(stderr, " %llu", hd[3 * 1024 + 32 + gq * 512 + r]); fprintf(stderr, "\n"); }
       fprintf(stderr, "[x] gens %u rounds %u dense %u deps %u nE0 %u |", st->generations, st->eval_rounds, st->dense_rounds, st->dependants, nE);

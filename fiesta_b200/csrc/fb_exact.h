@@ -39,6 +39,7 @@ struct FbExact {
   uint32_t *W[3], *F[3];       // work lists / flip lists, rotating per round
   uint32_t *wstamp;            // per entry: round for which it is already in a work list
   uint32_t *slotc;             // SMALL generations: codes of the owned slots
+  unsigned dense_min;          // work lists longer than this are evaluated through refreshed summaries (one wave of warps)
   unsigned small_max;          // generations up to this many entries run without summaries
   FbXCtl *d_ctl, *h_ctl;
   unsigned long long *d_dbg;

@@ -847,6 +847,65 @@ int fiesta_get_dist_grad_trilinear_batch(fiesta_map *m, const double *pos, int64
   return run_query(m, pos, n, 1, out, grad);
 }
 
+// ---- planner query plan: fixed batch size, pinned host buffers, the copy-in / kernel / copy-out sequence captured once as a
+// CUDA graph; a run is one graph launch + one stream synchronisation.
+struct fiesta_query_plan {
+  fiesta_map *m;
+  int64_t n;
+  double *h_pos, *h_out;        // pinned: [3n] positions; [n] distances followed by [3n] gradients
+  double *d_pos, *d_out;
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+};
+void fiesta_query_plan_destroy(fiesta_query_plan *p) {
+  if (!p) return;
+  cudaSetDevice(p->m->device);
+  cudaStreamSynchronize(p->m->stream);
+  if (p->exec) cudaGraphExecDestroy(p->exec);
+  if (p->graph) cudaGraphDestroy(p->graph);
+  if (p->h_pos) cudaFreeHost(p->h_pos);
+  if (p->h_out) cudaFreeHost(p->h_out);
+  if (p->d_pos) cudaFree(p->d_pos);
+  if (p->d_out) cudaFree(p->d_out);
+  delete p;
+}
+int fiesta_query_plan_create(fiesta_map *m, int64_t n, fiesta_query_plan **out) {
+  if (!m || !out || n <= 0) { set_error("fiesta_query_plan_create: bad argument"); return FIESTA_ERR_INVALID; }
+  if (!m->params_set) { set_error("fiesta_query_plan_create: call SetParameters first (the occupancy threshold is captured)"); return FIESTA_ERR_INVALID; }
+  *out = nullptr;
+  CK(cudaSetDevice(m->device));
+  fiesta_query_plan *p = new (std::nothrow) fiesta_query_plan();
+  if (!p) return FIESTA_ERR_INVALID;
+  memset((void *)p, 0, sizeof(*p));
+  p->m = m; p->n = n;
+#define CKP(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s failed: %s", #call, cudaGetErrorString(e__)); fiesta_query_plan_destroy(p); return FIESTA_ERR_CUDA; } } while (0)
+  CKP(cudaMallocHost((void **)&p->h_pos, (size_t)n * 3 * sizeof(double)));
+  CKP(cudaMallocHost((void **)&p->h_out, (size_t)n * 4 * sizeof(double)));
+  CKP(cudaMalloc((void **)&p->d_pos, (size_t)n * 3 * sizeof(double)));
+  CKP(cudaMalloc((void **)&p->d_out, (size_t)n * 4 * sizeof(double)));
+  CKP(cudaStreamSynchronize(m->stream));
+  CKP(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+  cudaMemcpyAsync(p->d_pos, p->h_pos, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, m->stream);
+  k_query<<<(unsigned)((n + 127) / 128), 128, 0, m->stream>>>(m->g, m->cobs, m->occ, m->l_occ, p->d_pos, n, 1, p->d_out, p->d_out + n);
+  cudaMemcpyAsync(p->h_out, p->d_out, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, m->stream);
+  CKP(cudaStreamEndCapture(m->stream, &p->graph));
+  CKP(cudaGraphInstantiate(&p->exec, p->graph, 0));
+#undef CKP
+  *out = p;
+  return FIESTA_OK;
+}
+double *fiesta_query_plan_positions(fiesta_query_plan *p) { return p ? p->h_pos : nullptr; }
+const double *fiesta_query_plan_distances(const fiesta_query_plan *p) { return p ? p->h_out : nullptr; }
+const double *fiesta_query_plan_gradients(const fiesta_query_plan *p) { return p ? p->h_out + p->n : nullptr; }
+int fiesta_query_plan_run(fiesta_query_plan *p) {
+  if (!p) return FIESTA_ERR_INVALID;
+  CK(cudaSetDevice(p->m->device));
+  CK(cudaGraphLaunch(p->exec, p->m->stream));
+  p->m->st.kernel_launches++;
+  CK(cudaStreamSynchronize(p->m->stream));
+  return FIESTA_OK;
+}
+
 // ---- exports
 static int run_export(fiesta_map *m, double *dist, int *cobs3, double *occ, int *hit, int *tot) {
   CK(cudaSetDevice(m->device));

@@ -29,7 +29,6 @@
 #define X_PUSH 2ull
 #define XMB_NONE 0xffffffffffffffffull
 #define X_NOFF 129
-#define X_DENSE_MIN 4096u
 #define XGB 8                         // writer words loaded per batch by a gather (24 / XGB batches)
 #define XDBG_GENS 1024                // trace layout (FIESTA_DEBUG_X): [3 * XDBG_GENS] per generation {nE, rounds, cycles},
 #define XDBG_PHASE (3 * XDBG_GENS)    // then 16 x {cycles, count} per phase category, then 2 x 512 work-list sizes per round
@@ -174,7 +173,7 @@ struct XArgs {
   uint32_t *wstamp;
   uint32_t *slotc;          // SMALL mode: winner codes, [small_max][32]
   FbXCtl *ctl;
-  unsigned nE0, small_max;  // nE0: insert seeds already in E[0]
+  unsigned nE0, small_max, dense_min;  // nE0: insert seeds already in E[0]
   // E2 (delete loop): dependants of deleted obstacles in the order of the reference's list walk
   const uint32_t *deps; unsigned ndep;
   uint32_t *ord;            // per voxel: position in deps, or XNONE
@@ -320,6 +319,8 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
     for (int q = 0; q < 32; ++q) x_gsync(&ctl->bar, bar_target);
     if (gtid == 0) a.dbg[XDBG_PHASE + 2 * 11] = (unsigned long long)(clock64() - t0) / 32ull;
   }
+  long long t_ph = a.dbg ? clock64() : 0;
+#define X_LAP(cat) do { if (a.dbg && gtid == 0) { const long long t_now = clock64(); a.dbg[XDBG_PHASE + 2 * (cat)] += (unsigned long long)(t_now - t_ph); a.dbg[XDBG_PHASE + 2 * (cat) + 1] += 1ull; t_ph = t_now; } } while (0)
   // ---- E2, second half: re-seed the dependants of the deleted obstacles (fixpoint over work lists, in place), then append
   // the re-seeded ones, in list-walk order, to the insert seeds in E[0] (:301-334).
   unsigned reseed_rounds = 0;
@@ -362,6 +363,7 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
       }
       x_gsync(&ctl->bar, bar_target);
     }
+    X_LAP(12);
     const unsigned per = (a.ndep + G - 1u) / G;
     const unsigned lo = min(a.ndep, b * per), hi = min(a.ndep, lo + per);
     unsigned mine = 0;
@@ -395,6 +397,7 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
     }
     nE += sh.total;
     x_gsync(&ctl->bar, bar_target);
+    X_LAP(13);
   }
   bool big = nE > a.small_max;
 
@@ -410,8 +413,6 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
   }
   x_gsync(&ctl->bar, bar_target);
 
-  long long t_ph = a.dbg ? clock64() : 0;
-#define X_LAP(cat) do { if (a.dbg && gtid == 0) { const long long t_now = clock64(); a.dbg[XDBG_PHASE + 2 * (cat)] += (unsigned long long)(t_now - t_ph); a.dbg[XDBG_PHASE + 2 * (cat) + 1] += 1ull; t_ph = t_now; } } while (0)
   while (nE) {
     const long long t_gen = a.dbg ? clock64() : 0;
     X_LAP(10);
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
       if (gtid == 0) { ctl->nW[zz] = 0; ctl->nF[zz] = 0; }
       if (r > 1u && nw == 0u && nf == 0u) break;
       ++rounds; ++wclock;
-      const bool dense = big && r > 1u && nw > X_DENSE_MIN;   // more than one wave of warps: evaluate through the summaries
+      const bool dense = big && r > 1u && nw > a.dense_min;   // more than one wave of warps: evaluate through the summaries
       if (dense) {                                             // bring the summaries up to date first, then evaluate through them
         ++dense_total;
         if (nf < nE / 4u) {                                    // few flips: only the targets of last round's flips
@@ -629,7 +630,7 @@ cudaError_t fb_xrelax_launch(FbExact *X, const FbGeom &g, uint32_t *cobs, unsign
   a.g = g; a.cobs = cobs; a.MB = X->MB; a.LS = X->LS; a.SUM = X->SUM; a.SUMg = X->SUMg;
   a.E[0] = X->E[0]; a.E[1] = X->E[1]; a.emask = X->emask;
   for (int k = 0; k < 3; ++k) { a.W[k] = X->W[k]; a.F[k] = X->F[k]; }
-  a.wstamp = X->wstamp; a.slotc = X->slotc; a.ctl = X->d_ctl; a.nE0 = nE0; a.small_max = X->small_max; a.dbg = dbg;
+  a.wstamp = X->wstamp; a.slotc = X->slotc; a.ctl = X->d_ctl; a.nE0 = nE0; a.small_max = X->small_max; a.dense_min = X->dense_min; a.dbg = dbg;
   void *args[] = {(void *)&a};
   return cudaLaunchCooperativeKernel((void *)k_x_relax, dim3(X->relax_blocks), dim3(XT), args, 0, s);
 }

@@ -160,6 +160,20 @@ int fiesta_get_distance_batch_pos(fiesta_map *m, const double *pos_xyz, int64_t 
 int fiesta_get_dist_grad_trilinear_batch(fiesta_map *m, const double *pos_xyz, int64_t n, double *out_dist,
                                          double *out_grad_xyz);
 
+/* Planner query plan: GetDistWithGradTrilinear (ESDFMap.cpp:481-540) for a FIXED number of positions per
+ * call, as trajectory optimisers issue it every iteration.  The plan owns pinned host buffers and a CUDA graph of
+ * {copy positions in, query kernel, copy distances + gradients out}; a run is one graph launch and one synchronisation.
+ * Write the n positions to fiesta_query_plan_positions() (xyz triples), call fiesta_query_plan_run(), read n distances and n
+ * gradient triples.  Results equal fiesta_get_dist_grad_trilinear_batch bit for bit.  Create it after SetParameters; destroy it
+ * before the map. */
+typedef struct fiesta_query_plan fiesta_query_plan;
+int fiesta_query_plan_create(fiesta_map *m, int64_t n, fiesta_query_plan **out);
+void fiesta_query_plan_destroy(fiesta_query_plan *p);
+double *fiesta_query_plan_positions(fiesta_query_plan *p);
+const double *fiesta_query_plan_distances(const fiesta_query_plan *p);
+const double *fiesta_query_plan_gradients(const fiesta_query_plan *p);
+int fiesta_query_plan_run(fiesta_query_plan *p);
+
 /* ---- state dumps in the reference's own representation (parity harness; host pointers, grid_total_size entries) ---- */
 int fiesta_export_distance(fiesta_map *m, double *out);             /* distance_buffer_: -10000 unknown, +10000 unreached */
 int fiesta_export_closest_obstacle(fiesta_map *m, int *out_xyz);    /* closest_obstacle_: 3 ints, -10000 = none */

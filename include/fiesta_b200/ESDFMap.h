@@ -117,6 +117,13 @@ class ESDFMap {
   void GetDistWithGradTrilinearBatch(const double *pos_xyz, long n, double *dist, double *grad_xyz) {
     check(fiesta_get_dist_grad_trilinear_batch(h_, pos_xyz, n, dist, grad_xyz), "GetDistWithGradTrilinearBatch");
   }
+  // Fixed-size variant for optimiser loops: pinned buffers + one CUDA-graph launch per call (fiesta_query_plan_* in
+  // fiesta_b200.h): fill fiesta_query_plan_positions(p), fiesta_query_plan_run(p), read distances / gradients.
+  fiesta_query_plan *MakeQueryPlan(long n) {
+    fiesta_query_plan *p = nullptr;
+    check(fiesta_query_plan_create(h_, n, &p), "MakeQueryPlan");
+    return p;
+  }
 
   // ---- visualisation (ESDFMap.h:144-145): flag pass + ordered stream compaction on the device, only the selected points
   // cross PCIe (fiesta_get_point_cloud / fiesta_get_slice_marker) ----

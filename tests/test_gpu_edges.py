@@ -143,6 +143,14 @@ def test_local_map_moving_box_exact(oracle_built):
     q = rng.uniform(-2.5, 2.5, (256, 3)) * (1, 1, 0.5)
     d1, g1 = dev.GetDistWithGradTrilinearBatch(q); d2, g2 = ora.GetDistWithGradTrilinearBatch(q)
     assert np.array_equal(d1, d2) and np.array_equal(g1, g2)
+    # the CUDA-graph query plan (fiesta_query_plan_*) returns the same bits, run after run
+    plan = dev.QueryPlan(256)
+    for rep in range(3):
+        qq = q if rep == 0 else rng.uniform(-3.3, 3.3, (256, 3)) * (1, 1, 0.5)   # incl. positions outside the map (-1 / sentinels)
+        d3, g3 = plan.run(qq)
+        d4, g4 = ora.GetDistWithGradTrilinearBatch(qq)
+        assert np.array_equal(d3, d4) and np.array_equal(g3, g4), rep
+    plan.close()
 
 
 def test_device_resident_event_batch(oracle_built):
