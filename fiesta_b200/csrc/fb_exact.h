@@ -4,7 +4,7 @@
 #include "fb_common.cuh"
 
 #define FB_X_MAX_BLOCKS 256
-#define FB_X_SMALL_DEFAULT 4096u
+#define FB_X_SMALL_DEFAULT 32768u   // (from a sweep on the 512^3 LIDAR frames; FIESTA_X_SMALL / FIESTA_X_DENSE override)
 #define FB_X_DBG_WORDS (3 * 1024 + 32 + 2 * 512)
 
 struct FbExactStats {

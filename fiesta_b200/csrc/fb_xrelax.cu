@@ -29,6 +29,7 @@
 #define X_PUSH 2ull
 #define XMB_NONE 0xffffffffffffffffull
 #define X_NOFF 129
+#define X_MAX_ROUNDS 4000000u
 #define XGB 8                         // writer words loaded per batch by a gather (24 / XGB batches)
 #define XDBG_GENS 1024                // trace layout (FIESTA_DEBUG_X): [3 * XDBG_GENS] per generation {nE, rounds, cycles},
 #define XDBG_PHASE (3 * XDBG_GENS)    // then 16 x {cycles, count} per phase category, then 2 x 512 work-list sizes per round
@@ -331,6 +332,47 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
       if (gtid == 0) ctl->nW[zz] = 0;
       if (r > 1u && nw == 0u) break;
       ++reseed_rounds; ++wclock;
+      if (nw <= 2u * gwarps) {
+        // short list: one WARP per dependant, lane k = neighbour k -- the 24 look-ups (position in deps, code, Exist bit) run side
+        // by side (three round trips instead of up to 72 one after the other); the round's length is what the sweep costs
+        for (unsigned q = gwarp; q < nw; q += gwarps) {
+          const unsigned i = r == 1u ? q : __ldcg(&a.W[in][q]);
+          int x, y, z; x_coords(g, __ldcg(&a.deps[i]), x, y, z);
+          int dx = 0, dy = 0, dz = 0;
+          if (lane < 24u) x_unpack_off(sh.dir[lane], dx, dy, dz);
+          const int nx = x + dx, ny = y + dy, nz = z + dz;
+          const bool ing = lane < 24u && fb_in_grid(g, nx, ny, nz);
+          const long long nv = ing ? fb_ii(g, nx, ny, nz) : 0;
+          const unsigned o = ing ? __ldcg(&a.ord[nv]) : XNONE;
+          uint32_t c = 0;
+          if (ing && fb_in_range(g, nx, ny, nz)) {
+            if (o != XNONE) { if (o < i) c = __ldcg(&a.nc[o]); }
+            else c = __ldcg(&a.cobs[nv]) & FB_CODE_MASK;
+          }
+          bool ok = false;
+          if (c >= 2u) { int px, py, pz; fb_unpack(c, px, py, pz); const long long oi = fb_ii(g, px, py, pz); ok = (__ldg(&a.occbits[oi >> 5]) >> (oi & 31)) & 1u; }
+          const unsigned vm = __ballot_sync(0xffffffffu, ok);
+          const unsigned kc = vm ? (unsigned)(__ffs(vm) - 1) : 24u;                 // first valid neighbour in dirs_ order (:308-321)
+          const uint32_t res = vm ? __shfl_sync(0xffffffffu, c, (int)kc) : FB_INF;
+          uint32_t was = 0;
+          if (lane == 0) { was = __ldcg(&a.nc[i]); a.nk[i] = (uint8_t)kc; }
+          was = __shfl_sync(0xffffffffu, was, 0);
+          if (res == was) continue;
+          if (lane == 0) a.nc[i] = res;
+          bool push = ing && o != XNONE && o > i;                                  // later dependants that look at this one
+          if (push) {
+            const unsigned so = __ldcg(&a.wstamp[o]);
+            push = so != wclock;
+            if (push && r > 1u && so != wclock - 1u) {                              // stable choice of a dependant not evaluated this round (see below)
+              const unsigned ko = __ldcg(&a.nk[o]), kd = lane ^ 1u;
+              push = kd == ko || (kd < ko && res >= 2u);
+            }
+            push = push && atomicExch(&a.wstamp[o], wclock) != wclock;
+          }
+          const unsigned slot2 = fb_warp_append(&ctl->nW[out], push);
+          if (push) a.W[out][slot2] = o;
+        }
+      } else
       for (unsigned q = gtid; q < nw; q += gthreads) {
         const unsigned i = r == 1u ? q : __ldcg(&a.W[in][q]);
         int x, y, z; x_coords(g, __ldcg(&a.deps[i]), x, y, z);
@@ -432,6 +474,7 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
       const unsigned nf = (big && r > 1u) ? __ldcg(&ctl->nF[in]) : 0u;
       if (gtid == 0) { ctl->nW[zz] = 0; ctl->nF[zz] = 0; }
       if (r > 1u && nw == 0u && nf == 0u) break;
+      if (r > X_MAX_ROUNDS) { if (gtid == 0) ctl->err = 2u; break; }   // cannot happen (element i is final after i+1 rounds at the latest); never spin forever on a B200
       ++rounds; ++wclock;
       const bool dense = big && r > 1u && nw > a.dense_min;   // more than one wave of warps: evaluate through the summaries
       if (dense) {                                             // bring the summaries up to date first, then evaluate through them
@@ -492,6 +535,7 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
       if (a.dbg && gtid == 0 && generations <= 2u && rounds <= 512u) a.dbg[XDBG_ROUNDS + (generations - 1u) * 512u + (rounds - 1u)] = nw;
     }
     rounds_total += rounds;
+    if (rounds > X_MAX_ROUNDS) break;
 
     // ---- commit: per-element masks of owned slots, winner counts per CTA (CTA-contiguous ranges keep the order)
     const unsigned per = (nE + G - 1u) / G;
