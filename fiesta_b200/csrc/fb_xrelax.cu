@@ -515,7 +515,11 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
           a.MB[p] = nb;
           if (big) a.F[out][atomicAdd(&ctl->nF[out], 1u)] = i;
         }
-        for (unsigned o = lane; o < X_NOFF; o += 32u) {        // later elements whose inputs this element can touch
+        // later elements whose inputs this element can touch: a pushing element offers to its 24 neighbours, which the elements
+        // within the 129 offsets a+b read; a flip between "stale" and "pulls" (or of the pulled code) only changes the
+        // element's offer to its own voxel, which only its 24 neighbours read (the table starts with 0 and dirs_)
+        const unsigned nof = (x_mb_kind(old) == X_PUSH || x_mb_kind(nb) == X_PUSH) ? (unsigned)X_NOFF : 25u;
+        for (unsigned o = lane; o < nof; o += 32u) {
           int dx, dy, dz; x_unpack_off(sh.off[o], dx, dy, dz);
           const int nx = x + dx, ny = y + dy, nz = z + dz;
           bool push = false; unsigned j = 0;

@@ -134,9 +134,10 @@ static void relax(void){
         if(a>=nw){ refresh_targets(F[in][a-nw]); continue; }
         long i=wl[a]; totevals++;
         u64 nb=eval(i,use_sum); long p=E[cur][i];
-        if(nb!=MB[p]){ MB[p]=nb; if(big) F[out][nF[out]++]=(u32)i;
+        if(nb!=MB[p]){ int wide=mb_kind(MB[p])==K_PUSH||mb_kind(nb)==K_PUSH;   // only a pushing element reaches beyond its own voxel: 129 offsets, else {0} u dirs
+          MB[p]=nb; if(big) F[out][nF[out]++]=(u32)i;
           int x,y,z; vxyz(p,&x,&y,&z);
-          for(int o=0;o<nOFF;o++){ int nx=x+OFF[o][0],ny=y+OFF[o][1],nz=z+OFF[o][2]; if(!ing(nx,ny,nz)) continue; u64 w=MB[vi(nx,ny,nz)]; if(w==MB_NONE) continue; u32 j=mb_idx(w);
+          for(int o=0;o<(wide?nOFF:25);o++){ int nx=x+OFF[o][0],ny=y+OFF[o][1],nz=z+OFF[o][2]; if(!ing(nx,ny,nz)) continue; u64 w=MB[vi(nx,ny,nz)]; if(w==MB_NONE) continue; u32 j=mb_idx(w);
             if(j>(u32)i && wstamp[j]!=wclock){ wstamp[j]=wclock; W[out][nW[out]++]=j; } } } }
       free(ord);
       if(rounds>100000){printf("no convergence\n");exit(1);} }
