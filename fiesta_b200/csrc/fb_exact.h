@@ -5,7 +5,7 @@
 
 #define FB_X_MAX_BLOCKS 256
 #define FB_X_SMALL_DEFAULT 32768u   // (from a sweep on the 512^3 LIDAR frames; FIESTA_X_SMALL / FIESTA_X_DENSE override)
-#define FB_X_DBG_WORDS (3 * 1024 + 32 + 2 * 512)
+#define FB_X_DBG_WORDS (3 * 1024 + 32 + 2 * 512 + 4096)
 
 struct FbExactStats {
   unsigned long long expansions;      // == the reference's "Expanding N nodes" (ESDFMap.cpp:347,394)

@@ -34,6 +34,7 @@
 #define XDBG_GENS 1024                // trace layout (FIESTA_DEBUG_X): [3 * XDBG_GENS] per generation {nE, rounds, cycles},
 #define XDBG_PHASE (3 * XDBG_GENS)    // then 16 x {cycles, count} per phase category, then 2 x 512 work-list sizes per round
 #define XDBG_ROUNDS (XDBG_PHASE + 32)
+#define XDBG_WMAX (XDBG_ROUNDS + 1024)      // 4096 slots: per round of the fixpoint, the longest work time of any CTA (cycles)
 
 static __constant__ int x_dirs[24][3] = {
     {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
@@ -45,6 +46,8 @@ static __constant__ int x_off_c[X_NOFF];     // the distinct sums a+b, packed (d
 struct XShared {
   int off[X_NOFF];                    // copy of x_off_c (lane-varying index: shared memory, not the constant cache)
   int dir[32];                        // dirs_ packed the same way; entry 24 = (0,0,0)
+  unsigned char slot[25 * 24];        // index in off[] of (target t) - dirs_[k]: where the k-th writer of an element's target t sits
+  unsigned char self[32];             // index in off[] of target t itself (entry 24 = 0)
   unsigned red[XW], red2[XW];
   unsigned base, total;
 };
@@ -67,6 +70,8 @@ __device__ __forceinline__ unsigned long long x_mb_kind(unsigned long long w) { 
 __device__ __forceinline__ uint32_t x_mb_code(unsigned long long w) { return (uint32_t)(w & FB_CODE_MASK); }
 
 struct XState { unsigned d; uint32_t c; unsigned ts; };
+// Per-warp stage of one element's neighbourhood: the words at the 129 offsets and the records of its 25 targets.
+struct XNb { unsigned long long w[X_NOFF + 3]; uint32_t c[28]; };
 
 // Everything the kernel reads is written by other SMs between barriers: all loads bypass L1 (ld.global.cg).
 // State of voxel (x,y,z) as seen at time T (exclusive); *first = earliest timestamp of an offer that beats the snapshot.
@@ -228,6 +233,46 @@ __device__ __forceinline__ void x_refresh_summaries(const XArgs &a, const XShare
   if (redo) x_summarize(a.g, a.cobs, a.MB, a.SUM, nx, ny, nz);
 }
 
+// Lists, for the next round, the later elements among the first `nof` offsets around (x,y,z) (deduplicated by the per-entry
+// round stamp).  One warp; every stage issues its loads / atomics for all of a lane's <= 5 offsets before the next stage looks
+// at the results, so the whole search costs four round trips instead of four per offset, and ends with ONE append.
+__device__ __forceinline__ void x_list_affected(const XArgs &a, const XShared &sh, unsigned lane, unsigned i, int x, int y, int z, unsigned nof,
+                                                unsigned wclock, unsigned out) {
+  const FbGeom &g = a.g;
+  unsigned long long w[5];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) {
+    const unsigned o = lane + 32u * (unsigned)t;
+    w[t] = XMB_NONE;
+    if (o < nof) {
+      int dx, dy, dz; x_unpack_off(sh.off[o], dx, dy, dz);
+      const int nx = x + dx, ny = y + dy, nz = z + dz;
+      if (fb_in_grid(g, nx, ny, nz)) w[t] = __ldcg(&a.MB[fb_ii(g, nx, ny, nz)]);
+    }
+  }
+  unsigned j[5], st[5];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) {
+    j[t] = w[t] != XMB_NONE ? x_mb_idx(w[t]) : 0u;
+    st[t] = (w[t] != XMB_NONE && j[t] > i) ? __ldcg(&a.wstamp[j[t]]) : wclock;      // wclock = nothing to do
+  }
+  unsigned pm = 0;
+#pragma unroll
+  for (int t = 0; t < 5; ++t)
+    if (st[t] != wclock && atomicExch(&a.wstamp[j[t]], wclock) != wclock) pm |= 1u << t;
+  const unsigned cnt = (unsigned)__popc(pm);
+  unsigned incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
+  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0u) return;
+  unsigned base = 0;
+  if (lane == 0) base = atomicAdd(&a.ctl->nW[out], total);
+  base = __shfl_sync(0xffffffffu, base, 0) + incl - cnt;
+#pragma unroll
+  for (int t = 0; t < 5; ++t) if ((pm >> t) & 1u) a.W[out][base++] = j[t];
+}
+
 // Behaviour of element i (one warp; lanes 0..23 = neighbour k at pop time, lane 24 = the element itself).  Returns the new word.
 template <bool USE_SUM>
 __device__ __forceinline__ unsigned long long x_eval(const XArgs &a, const XShared &sh, unsigned lane, unsigned par, unsigned i, uint32_t p, int x, int y, int z) {
@@ -257,6 +302,119 @@ __device__ __forceinline__ unsigned long long x_eval(const XArgs &a, const XShar
   for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o); best = other < best ? other : best; }
   if (best == ~0ull) return x_mb(par, i, X_PUSH, sc);
   return x_mb(par, i, X_PULL, __shfl_sync(0xffffffffu, st.c, (int)(best & 0xffu)));
+}
+
+// ---- gathering evaluation through a per-warp stage ------------------------------------------------------------------------
+// One round of loads brings the words at all 129 offsets and the records of the 25 targets into shared memory; the 25 state
+// queries, the search for the elements a flip can touch and (SMALL generations) the slot masks then read the stage.  Every
+// dependent access to HBM costs a microsecond here (random accesses into GB-sized arrays), so this is what a round costs.
+__device__ __forceinline__ void x_stage(const XArgs &a, const XShared &sh, XNb &nb, unsigned lane, int x, int y, int z) {
+  const FbGeom &g = a.g;
+  unsigned long long w[5];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) {
+    const unsigned o = lane + 32u * (unsigned)t;
+    w[t] = XMB_NONE;
+    if (o < X_NOFF) {
+      int dx, dy, dz; x_unpack_off(sh.off[o], dx, dy, dz);
+      const int nx = x + dx, ny = y + dy, nz = z + dz;
+      if (fb_in_grid(g, nx, ny, nz)) w[t] = __ldcg(&a.MB[fb_ii(g, nx, ny, nz)]);
+    }
+  }
+  uint32_t c = 0;
+  if (lane < 25u) {
+    int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
+    const int nx = x + dx, ny = y + dy, nz = z + dz;
+    if (fb_in_grid(g, nx, ny, nz)) c = __ldcg(&a.cobs[fb_ii(g, nx, ny, nz)]);
+  }
+  __syncwarp();                                                // the previous element's readers are done
+#pragma unroll
+  for (int t = 0; t < 5; ++t) { const unsigned o = lane + 32u * (unsigned)t; if (o < X_NOFF) nb.w[o] = w[t]; }
+  if (lane < 25u) nb.c[lane] = c;
+  __syncwarp();
+}
+// state of target `lane` (of the staged element at x,y,z) at time T; (qx,qy,qz) = the target's coordinates
+__device__ __forceinline__ XState x_state_nb(const FbGeom &g, const XShared &sh, const XNb &nb, unsigned lane, int qx, int qy, int qz, unsigned T, uint32_t &snap) {
+  XState s;
+  const uint32_t raw = nb.c[lane];
+  snap = raw & FB_CODE_MASK;
+  s.c = snap; s.d = (raw & FB_DINF) ? 0xffffffffu : x_dist_of(qx, qy, qz, snap); s.ts = XNONE;
+  const unsigned d0 = s.d;
+  if (snap == FB_UNKNOWN) return s;                            // never observed: accepts nothing (:382)
+  if (fb_in_range(g, qx, qy, qz)) {                            // pushes only go to voxels inside the update box (:378)
+#pragma unroll 8
+    for (int k = 0; k < 24; ++k) {
+      const unsigned long long ww = nb.w[sh.slot[lane * 24u + (unsigned)k]];
+      if (ww == XMB_NONE || x_mb_kind(ww) != X_PUSH) continue;
+      const unsigned ts = x_mb_idx(ww) * 32u + (unsigned)k;
+      const uint32_t c = x_mb_code(ww);
+      const unsigned d = x_d2(qx, qy, qz, c);
+      if (d < d0 && ts < T && (d < s.d || (d == s.d && ts < s.ts))) { s.d = d; s.c = c; s.ts = ts; }
+    }
+  }
+  const unsigned long long wown = nb.w[sh.self[lane]];         // the entry's own pull is not range-checked (:349-367)
+  if (wown != XMB_NONE && x_mb_kind(wown) == X_PULL) {
+    const unsigned ts = x_mb_idx(wown) * 32u + 24u;
+    const uint32_t c = x_mb_code(wown);
+    const unsigned d = x_d2(qx, qy, qz, c);
+    if (d < d0 && ts < T && (d < s.d || (d == s.d && ts < s.ts))) { s.d = d; s.c = c; s.ts = ts; }
+  }
+  return s;
+}
+// behaviour of the staged element i (the same reduction as x_eval)
+__device__ __forceinline__ unsigned long long x_eval_nb(const XArgs &a, const XShared &sh, const XNb &nb, unsigned lane, unsigned par, unsigned i, int x, int y, int z) {
+  const FbGeom &g = a.g;
+  const unsigned T0 = i * 32u;
+  int qx = x, qy = y, qz = z;
+  bool valid = lane == 24;
+  if (lane < 24) {
+    int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
+    qx += dx; qy += dy; qz += dz;
+    valid = fb_in_range(g, qx, qy, qz) && fb_in_grid(g, qx, qy, qz);
+  }
+  XState st; st.d = 0xffffffffu; st.c = 0; st.ts = XNONE;
+  uint32_t snap = 0;
+  if (valid) st = x_state_nb(g, sh, nb, lane, qx, qy, qz, T0, snap);
+  const unsigned sd = __shfl_sync(0xffffffffu, st.d, 24);
+  const uint32_t sc = __shfl_sync(0xffffffffu, st.c, 24);
+  const uint32_t c0 = __shfl_sync(0xffffffffu, snap, 24);
+  if (sd != x_dist_of(x, y, z, c0)) return x_mb(par, i, X_DEAD, 0);   // stale (:345)
+  unsigned long long key = ~0ull;                              // pull phase (:349-367)
+  if (lane < 24 && valid && st.c >= 2u) {
+    const unsigned t = x_d2(x, y, z, st.c);
+    if (t < sd) key = ((unsigned long long)t << 8) | lane;
+  }
+  unsigned long long best = key;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o); best = other < best ? other : best; }
+  if (best == ~0ull) return x_mb(par, i, X_PUSH, sc);
+  return x_mb(par, i, X_PULL, __shfl_sync(0xffffffffu, st.c, (int)(best & 0xffu)));
+}
+// x_list_affected with the words taken from the stage (no reload)
+__device__ __forceinline__ void x_list_affected_nb(const XArgs &a, const XNb &nb, unsigned lane, unsigned i, unsigned nof, unsigned wclock, unsigned out) {
+  unsigned j[5], st[5];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) {
+    const unsigned o = lane + 32u * (unsigned)t;
+    const unsigned long long w = o < nof ? nb.w[o] : XMB_NONE;
+    j[t] = w != XMB_NONE ? x_mb_idx(w) : 0u;
+    st[t] = (w != XMB_NONE && j[t] > i) ? __ldcg(&a.wstamp[j[t]]) : wclock;
+  }
+  unsigned pm = 0;
+#pragma unroll
+  for (int t = 0; t < 5; ++t)
+    if (st[t] != wclock && atomicExch(&a.wstamp[j[t]], wclock) != wclock) pm |= 1u << t;
+  const unsigned cnt = (unsigned)__popc(pm);
+  unsigned incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
+  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0u) return;
+  unsigned base = 0;
+  if (lane == 0) base = atomicAdd(&a.ctl->nW[out], total);
+  base = __shfl_sync(0xffffffffu, base, 0) + incl - cnt;
+#pragma unroll
+  for (int t = 0; t < 5; ++t) if ((pm >> t) & 1u) a.W[out][base++] = j[t];
 }
 
 // Exclusive scan of one count per thread over the CTA (two block barriers); returns the CTA total in `total`.
@@ -296,6 +454,8 @@ __device__ __forceinline__ uint32_t x_reseed_eval(const XArgs &a, unsigned i, in
   return FB_INF;
 }
 
+extern __shared__ __align__(16) unsigned char x_dyn_smem[];
+
 __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
   __shared__ XShared sh;
   const FbGeom &g = a.g;
@@ -305,8 +465,20 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
   const unsigned gtid = b * XT + tid, gthreads = G * XT;
   const unsigned gwarp = gtid >> 5, gwarps = gthreads >> 5;
   for (unsigned k = tid; k < X_NOFF; k += XT) sh.off[k] = x_off_c[k];
+  if (tid < 32) sh.self[tid] = 0;
   if (tid < 32) sh.dir[tid] = tid < 24 ? ((x_dirs[tid][0] + 4) | ((x_dirs[tid][1] + 4) << 4) | ((x_dirs[tid][2] + 4) << 8)) : (4 | (4 << 4) | (4 << 8));
   __syncthreads();
+  for (unsigned q = tid; q < 25u * 24u + 25u; q += XT) {         // where target t's k-th writer (and t itself) sits among the 129 offsets
+    const unsigned t = q < 600u ? q / 24u : q - 600u, k = q < 600u ? q % 24u : 24u;
+    int tx, ty, tz, kx = 0, ky = 0, kz = 0; x_unpack_off(sh.dir[t], tx, ty, tz);
+    if (k < 24u) x_unpack_off(sh.dir[k], kx, ky, kz);
+    const int code = (tx - kx + 4) | ((ty - ky + 4) << 4) | ((tz - kz + 4) << 8);
+    unsigned found = 0;
+    for (unsigned o = 0; o < X_NOFF; ++o) if (sh.off[o] == code) found = o;
+    if (q < 600u) sh.slot[q] = (unsigned char)found; else sh.self[t] = (unsigned char)found;
+  }
+  __syncthreads();
+  XNb &stg = reinterpret_cast<XNb *>(x_dyn_smem)[wid];
 
   // grid-uniform state (every CTA computes the same values)
   unsigned nE = a.nE0, bar_target = 0;
@@ -495,6 +667,7 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
       const bool use_sum = big && (r == 1u || dense);
       const unsigned nref = (big && !dense) ? nf : 0u;
       const uint32_t *wl = a.W[in];
+      const long long t_w0 = a.dbg ? clock64() : 0;
       for (unsigned q = gwarp; q < nw + nref; q += gwarps) {
         if (q >= nw) {                                         // summaries of the targets of an element that flipped last round
           const unsigned i = __ldcg(&a.F[in][q - nw]);
@@ -506,9 +679,20 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
         const unsigned i = r == 1u ? q : __ldcg(&wl[q]);
         const uint32_t p = __ldcg(&E[i]);
         int x, y, z; x_coords(g, p, x, y, z);
+        if (!use_sum) {                                        // gathering evaluation: everything from one staged round of loads
+          x_stage(a, sh, stg, lane, x, y, z);
+          const unsigned long long old = stg.w[0], nw2 = x_eval_nb(a, sh, stg, lane, gen, i, x, y, z);
+          if (nw2 == old) continue;
+          if (lane == 0) {                                     // flip
+            a.MB[p] = nw2;
+            if (big) a.F[out][atomicAdd(&ctl->nF[out], 1u)] = i;
+          }
+          x_list_affected_nb(a, stg, lane, i, (x_mb_kind(old) == X_PUSH || x_mb_kind(nw2) == X_PUSH) ? (unsigned)X_NOFF : 25u, wclock, out);
+          continue;
+        }
         unsigned long long old = 0;
         if (lane == 0) old = __ldcg(&a.MB[p]);
-        const unsigned long long nb = use_sum ? x_eval<true>(a, sh, lane, gen, i, p, x, y, z) : x_eval<false>(a, sh, lane, gen, i, p, x, y, z);
+        const unsigned long long nb = x_eval<true>(a, sh, lane, gen, i, p, x, y, z);
         old = __shfl_sync(0xffffffffu, old, 0);
         if (nb == old) continue;
         if (lane == 0) {                                       // flip
@@ -518,22 +702,9 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
         // later elements whose inputs this element can touch: a pushing element offers to its 24 neighbours, which the elements
         // within the 129 offsets a+b read; a flip between "stale" and "pulls" (or of the pulled code) only changes the
         // element's offer to its own voxel, which only its 24 neighbours read (the table starts with 0 and dirs_)
-        const unsigned nof = (x_mb_kind(old) == X_PUSH || x_mb_kind(nb) == X_PUSH) ? (unsigned)X_NOFF : 25u;
-        for (unsigned o = lane; o < nof; o += 32u) {
-          int dx, dy, dz; x_unpack_off(sh.off[o], dx, dy, dz);
-          const int nx = x + dx, ny = y + dy, nz = z + dz;
-          bool push = false; unsigned j = 0;
-          if (fb_in_grid(g, nx, ny, nz)) {
-            const unsigned long long w = __ldcg(&a.MB[fb_ii(g, nx, ny, nz)]);
-            if (w != XMB_NONE) {
-              j = x_mb_idx(w);
-              push = j > i && __ldcg(&a.wstamp[j]) != wclock && atomicExch(&a.wstamp[j], wclock) != wclock;
-            }
-          }
-          const unsigned slot = fb_warp_append(&ctl->nW[out], push);
-          if (push) a.W[out][slot] = j;
-        }
+        x_list_affected(a, sh, lane, i, x, y, z, (x_mb_kind(old) == X_PUSH || x_mb_kind(nb) == X_PUSH) ? (unsigned)X_NOFF : 25u, wclock, out);
       }
+      if (a.dbg) { __syncthreads(); if (tid == 0) atomicMax(&a.dbg[XDBG_WMAX + ((rounds_total + rounds) & 4095u)], (unsigned long long)(clock64() - t_w0)); }
       x_gsync(&ctl->bar, bar_target);
       X_LAP(big ? (r == 1u ? 1 : (dense ? 3 : 2)) : (r == 1u ? 6 : 7));
       if (a.dbg && gtid == 0 && generations <= 2u && rounds <= 512u) a.dbg[XDBG_ROUNDS + (generations - 1u) * 512u + (rounds - 1u)] = nw;
@@ -549,8 +720,8 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
       const uint32_t p = __ldcg(&E[i]);
       int x, y, z; x_coords(g, p, x, y, z);
       unsigned long long w = 0;
-      if (lane == 0) w = __ldcg(&a.MB[p]);
-      w = __shfl_sync(0xffffffffu, w, 0);
+      if (!big) { x_stage(a, sh, stg, lane, x, y, z); w = stg.w[0]; }
+      else { if (lane == 0) w = __ldcg(&a.MB[p]); w = __shfl_sync(0xffffffffu, w, 0); }
       const unsigned long long kind = x_mb_kind(w);
       bool win = false;
       if ((kind == X_PUSH && lane < 24) || (kind == X_PULL && lane == 24)) {
@@ -560,8 +731,8 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
           const unsigned ts = i * 32u + lane;
           if (big) win = __ldcg(&a.SUM[fb_ii(g, nx, ny, nz)]).y == ts;
           else {
-            unsigned first; uint32_t snap;
-            const XState f = x_gather<false>(g, a.cobs, a.MB, nx, ny, nz, XNONE, first, snap);
+            uint32_t snap;
+            const XState f = x_state_nb(g, sh, stg, lane, nx, ny, nz, XNONE, snap);
             win = f.ts == ts;
             if (win) a.slotc[ts] = f.c;
           }
@@ -666,7 +837,7 @@ cudaError_t fb_xrelax_init() {
 
 int fb_xrelax_blocks(int device) {
   int per_sm = 0, sms = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_x_relax, XT, 0) != cudaSuccess || per_sm < 1) return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_x_relax, XT, sizeof(XNb) * XW) != cudaSuccess || per_sm < 1) return -1;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
   return sms;                                                  // one CTA per SM: the barrier is cheapest with few arrivals
 }
@@ -680,5 +851,5 @@ cudaError_t fb_xrelax_launch(FbExact *X, const FbGeom &g, uint32_t *cobs, unsign
   for (int k = 0; k < 3; ++k) { a.W[k] = X->W[k]; a.F[k] = X->F[k]; }
   a.wstamp = X->wstamp; a.slotc = X->slotc; a.ctl = X->d_ctl; a.nE0 = nE0; a.small_max = X->small_max; a.dense_min = X->dense_min; a.dbg = dbg;
   void *args[] = {(void *)&a};
-  return cudaLaunchCooperativeKernel((void *)k_x_relax, dim3(X->relax_blocks), dim3(XT), args, 0, s);
+  return cudaLaunchCooperativeKernel((void *)k_x_relax, dim3(X->relax_blocks), dim3(XT), args, sizeof(XNb) * XW, s);
 }
