@@ -200,6 +200,17 @@ cudaError_t fb_exact_init(FbExact *X, const FbGeom &g, int device, cudaStream_t 
   X->small_max = FB_X_SMALL_DEFAULT;
   if (const char *e = getenv("FIESTA_X_SMALL")) { long v = atol(e); if (v >= 0 && v <= 65536) X->small_max = (unsigned)v; }
   XCK(cudaMalloc((void **)&X->slotc, ((size_t)X->small_max + 1) * 32 * 4));
+  // Per-frame work arrays (touched voxels, dependants of deleted obstacles, sort scratch) are sized up front for 1/8 of the
+  // grid: growing them on demand puts cudaMalloc / cudaFree (device-wide synchronisations, milliseconds) inside UpdateESDF.
+  {
+    const size_t c0 = P / 8 > (1u << 20) ? P / 8 : (1u << 20);
+    cudaError_t e;
+    if ((e = x_ensure(X, &X->k1, &X->cap_k1, c0)) || (e = x_ensure(X, &X->k2, &X->cap_k2, c0)) || (e = x_ensure(X, &X->k1b, &X->cap_k1b, c0)) ||
+        (e = x_ensure(X, &X->k2b, &X->cap_k2b, c0)) || (e = x_ensure(X, &X->dv, &X->cap_dv, c0)) || (e = x_ensure(X, &X->idx[0], &X->cap_idx[0], c0)) ||
+        (e = x_ensure(X, &X->idx[1], &X->cap_idx[1], c0)) || (e = x_ensure(X, &X->deps, &X->cap_deps, c0)) || (e = x_ensure(X, &X->nc[0], &X->cap_nc[0], c0)) ||
+        (e = x_ensure(X, &X->nc[1], &X->cap_nc[1], c0)) || (e = x_ensure(X, &X->flags, &X->cap_flags, c0)) || (e = x_ensure(X, &X->flags2, &X->cap_flags2, c0)) ||
+        (e = x_ensure(X, &X->sel, &X->cap_sel, c0)) || (e = x_tmp(X, c0 * 16 + (64u << 20)))) return e;
+  }
   XCK(cudaMalloc((void **)&X->d_ctl, sizeof(FbXCtl))); XCK(cudaMemsetAsync(X->d_ctl, 0, sizeof(FbXCtl), s));
   XCK(cudaMallocHost((void **)&X->h_ctl, sizeof(FbXCtl)));
   XCK(cudaMalloc((void **)&X->d_count, 16)); XCK(cudaMalloc((void **)&X->d_flag, 16));
