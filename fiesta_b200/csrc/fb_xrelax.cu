@@ -1,22 +1,30 @@
-// fiesta_b200 -- ORDER-EXACT mode, E3: the FIFO relaxation loop of UpdateESDF (/root/reference/src/ESDFMap.cpp:338-392) as ONE
-// persistent kernel, k_x_relax: every FIFO generation, every round of its behaviour fixpoint and the ordered hand-over to
-// the next generation run on the device, separated by grid barriers; the host launches it once per UpdateESDF and reads
-// one control block back.  (CPU model of exactly this formulation: oracle/exact_model.c.)
+// fiesta_b200 -- ORDER-EXACT mode, E2 (second half) + E3: the re-seeding of the delete loop and the FIFO relaxation loop of
+// UpdateESDF (/root/reference/src/ESDFMap.cpp:301-334, 338-392) as ONE persistent kernel, k_x_relax: every FIFO generation,
+// every round of its behaviour fixpoint and the ordered hand-over to the next generation run on the device, separated by
+// grid barriers; the host launches it once per UpdateESDF and reads one control block back.
+// (CPU model of exactly this formulation, checked against the sequential reference: oracle/exact_model.c.)
 //
 //  * A FIFO generation is one list E of voxels in queue order.  Element i, direction k acts at the timestamp 32*i + k
 //    (its pull at 32*i + 24).  MB[v] is the packed word {queue position, behaviour, code} of the live entry at voxel v.
 //  * state(v, T): what voxel v holds at time T = the snapshot, or the lexicographic minimum (distance, timestamp) over the
 //    offers with timestamp < T of the <= 25 elements that can write v which beat the snapshot -- exactly what a sequence
-//    of strict `>` tests in timestamp order leaves behind (x_gather).  BIG generations cache, per target voxel, a summary
-//    {first improving timestamp, best timestamp, best code, snapshot code}; a query gathers only if first < T <= best.
-//  * An element's behaviour (stale / pulled code / pushes code, :345-373) depends only on states at its own pop time.
-//    Round 1 evaluates every element against the guess "everybody pushes its snapshot code"; a flip lists every LATER
-//    element whose inputs it can touch (the 129 offsets a+b, a,b in {0} u dirs_) for the next round, and later rounds only
-//    evaluate their list (by gathering; a dense list first recomputes all summaries).  Element i is right once all
+//    of strict `>` tests in timestamp order leaves behind (x_gather / x_state_nb).  BIG generations cache, per target voxel,
+//    a summary {first improving timestamp, best timestamp, best code, snapshot code}, computed once per pass by whoever
+//    stamps the target first (x_claim_summaries); a query gathers only if first < T <= best.
+//  * An element's behaviour (stale / pulled code / pushes code, :345-373) depends only on states at its own pop time, i.e.
+//    on the words at the 129 offsets a+b (a,b in {0} u dirs_) around it.  Round 1 evaluates every element against the guess
+//    "everybody pushes its snapshot code"; a flip lists every LATER element it can touch for the next round (all 129 offsets
+//    if pushing is involved, else only the 24 neighbours: just the offer to its own voxel changed).  Short lists are evaluated
+//    from a per-warp shared-memory stage filled by one round of loads (x_stage) while last round's flips refresh the
+//    summaries of their targets; long lists first refresh, then evaluate through the summaries.  Element i is right once all
 //    earlier ones are, so the fixpoint -- reached by a round without flips, which has only read final words -- is the
-//    sequential execution.  In BIG mode the summaries of a flipped element's targets are recomputed during the next round.
-//  * Commit: element i owns slot k iff the final state of its k-th target carries the timestamp 32*i + k; the owned slots in
-//    timestamp order (per-element masks, exclusive scan over CTA-contiguous ranges) are the next generation.
+//    sequential execution.
+//  * Hand-over: element i owns slot k iff the final state of its k-th target carries the timestamp 32*i + k; the owned slots in
+//    timestamp order (per-element masks, exclusive scan over CTA-contiguous ranges) are the next generation; old words are
+//    retired by compare-and-swap (a generation-parity bit tells old from new).
+//  * Before generation 0 the same kernel iterates the delete loop's re-seeding ("first valid neighbour in dirs_ order",
+//    earlier dependants expose their new value, :308-321) to its fixpoint over work lists and appends the re-seeded
+//    dependants, in list-walk order, to the insert seeds.
 #include <stdio.h>
 #include "fb_common.cuh"
 #include "fb_exact.h"
