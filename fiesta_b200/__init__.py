@@ -65,6 +65,9 @@ SYMBOLS = [
     "fiesta_get_stats", "fiesta_synchronize", "fiesta_set_shard", "fiesta_shard_pack", "fiesta_shard_ingest", "fiesta_shard_relax", "fiesta_get_point_cloud", "fiesta_get_slice_marker", "fiesta_set_occupancy_batch_vox_device", "fiesta_depth_frame", "fiesta_last_depth_cloud",
     "fiesta_query_plan_create", "fiesta_query_plan_destroy", "fiesta_query_plan_positions", "fiesta_query_plan_distances",
     "fiesta_query_plan_gradients", "fiesta_query_plan_run",
+    "fiesta_host_mirror_create", "fiesta_host_mirror_destroy", "fiesta_host_mirror_refresh", "fiesta_host_mirror_get_distance_pos",
+    "fiesta_host_mirror_get_distance_vox", "fiesta_host_mirror_get_dist_grad_trilinear", "fiesta_host_mirror_get_distance_batch_pos",
+    "fiesta_host_mirror_get_dist_grad_trilinear_batch", "fiesta_host_mirror_records", "fiesta_host_mirror_stats",
 ]
 
 _lib = None
@@ -92,6 +95,21 @@ def load_library():
         L.fiesta_query_plan_destroy.argtypes = [C.c_void_p]
         L.fiesta_query_plan_destroy.restype = None
         L.fiesta_query_plan_run.argtypes = [C.c_void_p]
+        L.fiesta_host_mirror_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.fiesta_host_mirror_destroy.argtypes = [C.c_void_p]
+        L.fiesta_host_mirror_destroy.restype = None
+        L.fiesta_host_mirror_refresh.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.fiesta_host_mirror_get_distance_pos.argtypes = [C.c_void_p, C.c_void_p]
+        L.fiesta_host_mirror_get_distance_pos.restype = C.c_double
+        L.fiesta_host_mirror_get_distance_vox.argtypes = [C.c_void_p, C.c_void_p]
+        L.fiesta_host_mirror_get_distance_vox.restype = C.c_double
+        L.fiesta_host_mirror_get_dist_grad_trilinear.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fiesta_host_mirror_get_dist_grad_trilinear.restype = C.c_double
+        L.fiesta_host_mirror_get_distance_batch_pos.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.fiesta_host_mirror_get_dist_grad_trilinear_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.fiesta_host_mirror_records.argtypes = [C.c_void_p]
+        L.fiesta_host_mirror_records.restype = C.POINTER(C.c_uint32)
+        L.fiesta_host_mirror_stats.argtypes = [C.c_void_p, C.c_void_p]
         for n in ("fiesta_query_plan_positions", "fiesta_query_plan_distances", "fiesta_query_plan_gradients"):
             getattr(L, n).argtypes = [C.c_void_p]
             getattr(L, n).restype = C.POINTER(C.c_double)
@@ -124,6 +142,57 @@ class QueryPlan:
     def close(self):
         if self._h:
             self._m._L.fiesta_query_plan_destroy(self._h)
+            self._h = None
+
+
+class HostMirror:
+    """fiesta_host_mirror: the distance records in pinned host memory, patched from the device by refresh(); the getters are
+    pure host code (no CUDA call) and return the bits of the device queries as of the last refresh."""
+
+    def __init__(self, m):
+        self._m = m
+        h = C.c_void_p()
+        m._ck(m._L.fiesta_host_mirror_create(m._h, C.byref(h)), "fiesta_host_mirror_create")
+        self._h = h
+
+    def refresh(self):
+        n = C.c_int64(0)
+        self._m._ck(self._m._L.fiesta_host_mirror_refresh(self._h, C.byref(n)), "fiesta_host_mirror_refresh")
+        return n.value
+
+    def stats(self):
+        a = np.zeros(4, np.int64)
+        self._m._ck(self._m._L.fiesta_host_mirror_stats(self._h, a.ctypes), "fiesta_host_mirror_stats")
+        return dict(zip(("changed", "scanned", "refreshes", "full_copies"), (int(x) for x in a)))
+
+    def GetDistance(self, p):
+        if all(isinstance(x, (int, np.integer)) for x in p):
+            v = np.ascontiguousarray(p, dtype=np.int32)
+            return float(self._m._L.fiesta_host_mirror_get_distance_vox(self._h, v.ctypes))
+        return float(self._m._L.fiesta_host_mirror_get_distance_pos(self._h, _f64(p).ctypes))
+
+    def GetDistWithGradTrilinear(self, pos):
+        g = np.zeros(3)
+        d = float(self._m._L.fiesta_host_mirror_get_dist_grad_trilinear(self._h, _f64(pos).ctypes, g.ctypes))
+        return d, g
+
+    def GetDistanceBatch(self, pos):
+        pos = _f64(pos).reshape(-1, 3)
+        d = np.empty(len(pos))
+        self._m._ck(self._m._L.fiesta_host_mirror_get_distance_batch_pos(self._h, pos.ctypes, C.c_int64(len(pos)), d.ctypes), "mirror batch")
+        return d
+
+    def GetDistWithGradTrilinearBatch(self, pos):
+        pos = _f64(pos).reshape(-1, 3)
+        d = np.empty(len(pos))
+        g = np.empty((len(pos), 3))
+        self._m._ck(self._m._L.fiesta_host_mirror_get_dist_grad_trilinear_batch(self._h, pos.ctypes, C.c_int64(len(pos)), d.ctypes, g.ctypes),
+                    "mirror trilinear batch")
+        return d, g
+
+    def close(self):
+        if self._h:
+            self._m._L.fiesta_host_mirror_destroy(self._h)
             self._h = None
 
 
@@ -247,6 +316,10 @@ class ESDFMap:
     def QueryPlan(self, n):
         """Fixed-size GetDistWithGradTrilinear batch as a CUDA graph over pinned buffers (fiesta_query_plan_*)."""
         return QueryPlan(self, n)
+
+    def HostMirror(self):
+        """Pinned host copy of the distance records, patched by refresh() with the records UpdateESDF changed (fiesta_host_mirror_*)."""
+        return HostMirror(self)
 
     def RaycastFrame(self, xyz, T, min_ray_length, max_ray_length):
         """xyz: (n,3) float32 host array, or an integer device pointer paired with `n` as a tuple (ptr, n)."""

@@ -68,7 +68,19 @@ struct fiesta_map {
   FbExact X;
   unsigned n_xtouched;
   fiesta_stats st;
+  // pinned host mirror (next #3): union of the update boxes that were current while records could change
+  struct fiesta_host_mirror *mirror;
+  int dirty_lo[3], dirty_hi[3];
+  bool dirty_any, pending_obs;      // pending_obs: observations counted under the current box and not integrated yet
 };
+static void mark_dirty(fiesta_map *m) {                                   // tracked without a mirror too: events staged before a mirror is
+  const FbGeom &g = m->g;                                                   // created are integrated after it
+  for (int i = 0; i < 3; ++i) {
+    if (!m->dirty_any || g.min_vec[i] < m->dirty_lo[i]) m->dirty_lo[i] = g.min_vec[i];
+    if (!m->dirty_any || g.max_vec[i] > m->dirty_hi[i]) m->dirty_hi[i] = g.max_vec[i];
+  }
+  m->dirty_any = true;
+}
 
 // ====================================================================== kernels
 __global__ void k_reset_ray_ctr(FbCounters *c) {
@@ -160,7 +172,8 @@ __global__ void __launch_bounds__(128) k_integrate(FbGeom g, const uint32_t *til
 }
 
 // distance_buffer_ value of a record (ESDFMap.cpp:122-123, 198, 247): exact because the stored obstacle coordinate is exact.
-__device__ __forceinline__ double fb_record_distance(uint32_t c, int x, int y, int z, double res) {
+// Host + device: the pinned host mirror (fiesta_host_mirror_*) evaluates the same expression on the same records.
+__host__ __device__ __forceinline__ double fb_record_distance(uint32_t c, int x, int y, int z, double res) {
   const bool dinf = (c & FB_DINF) != 0u;                                    // between calls bit 31 is only ever set by EXACT mode's local-map reset
   c &= FB_CODE_MASK;
   if (c == FB_UNKNOWN) return (double)FIESTA_UNDEFINED;
@@ -190,33 +203,33 @@ __global__ void k_export(FbGeom g, const uint32_t *cobs, const double *occ, cons
 
 // GetDistance(Vector3i) (ESDFMap.cpp:477-479): unknown reads +infinity_.  Out-of-grid coordinates (undefined behaviour
 // in the reference) also read +infinity_.
-__device__ __forceinline__ double fb_get_distance_vox(const FbGeom &g, const uint32_t *cobs, int x, int y, int z) {
+__host__ __device__ __forceinline__ uint32_t fb_ld_record(const uint32_t *p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+__host__ __device__ __forceinline__ double fb_get_distance_vox(const FbGeom &g, const uint32_t *cobs, int x, int y, int z) {
   if (!fb_in_grid(g, x, y, z)) return (double)FIESTA_INFINITY;
-  const double d = fb_record_distance(__ldg(&cobs[fb_ii(g, x, y, z)]), x, y, z, g.res);
+  const double d = fb_record_distance(fb_ld_record(&cobs[fb_ii(g, x, y, z)]), x, y, z, g.res);
   return d < 0 ? (double)FIESTA_INFINITY : d;
 }
-__device__ __forceinline__ bool fb_pos_in_map(const FbGeom &g, const double *p) {
+__host__ __device__ __forceinline__ bool fb_pos_in_map(const FbGeom &g, const double *p) {
   if (p[0] < g.min_range[0] || p[1] < g.min_range[1] || p[2] < g.min_range[2]) return false;
   if (p[0] > g.max_range[0] || p[1] > g.max_range[1] || p[2] > g.max_range[2]) return false;
   return true;
 }
-
-// mode 0: GetDistance(Vector3d)  (ESDFMap.cpp:467-475)      out[i]
-// mode 1: GetDistWithGradTrilinear (ESDFMap.cpp:481-540)    out[i], grad[3i..]
-// mode 2: GetOccupancy(Vector3d)  (ESDFMap.cpp:452-460)      out[i] = 0/1/-10000
-__global__ void k_query(FbGeom g, const uint32_t *cobs, const double *occ, double l_occ, const double *pos, long long n, int mode,
-                        double *out, double *grad) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double p[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
-  if (mode == 0 || mode == 2) {
-    if (!fb_pos_in_map(g, p)) { out[i] = (double)FIESTA_UNDEFINED; return; }
-    const int x = (int)floor((p[0] - g.origin[0]) / g.res), y = (int)floor((p[1] - g.origin[1]) / g.res), z = (int)floor((p[2] - g.origin[2]) / g.res);
-    if (mode == 0) out[i] = fb_get_distance_vox(g, cobs, x, y, z);
-    else out[i] = fb_in_grid(g, x, y, z) ? (occ[fb_ii(g, x, y, z)] > l_occ ? 1.0 : 0.0) : 0.0;
-    return;
-  }
-  if (!fb_pos_in_map(g, p)) { out[i] = -1.0; grad[3 * i] = grad[3 * i + 1] = grad[3 * i + 2] = 0.0; return; }
+// GetDistance(Vector3d) (ESDFMap.cpp:467-475)
+__host__ __device__ __forceinline__ double fb_query_distance(const FbGeom &g, const uint32_t *cobs, const double *p) {
+  if (!fb_pos_in_map(g, p)) return (double)FIESTA_UNDEFINED;
+  const int x = (int)floor((p[0] - g.origin[0]) / g.res), y = (int)floor((p[1] - g.origin[1]) / g.res), z = (int)floor((p[2] - g.origin[2]) / g.res);
+  return fb_get_distance_vox(g, cobs, x, y, z);
+}
+// GetDistWithGradTrilinear (ESDFMap.cpp:481-540), operation for operation (fp64, no contraction: -fmad=false on the device,
+// no FMA target on the host).
+__host__ __device__ __forceinline__ double fb_query_trilinear(const FbGeom &g, const uint32_t *cobs, const double *p, double *grad) {
+  if (!fb_pos_in_map(g, p)) { grad[0] = grad[1] = grad[2] = 0.0; return -1.0; }
   int b[3];
   double bp[3], f[3];
 #pragma unroll
@@ -239,15 +252,35 @@ __global__ void k_query(FbGeom g, const uint32_t *cobs, const double *occ, doubl
   const double v11 = (1 - f[0]) * c[0][1][1] + f[0] * c[1][1][1];
   const double v0 = (1 - f[1]) * v00 + f[1] * v10;
   const double v1 = (1 - f[1]) * v01 + f[1] * v11;
-  out[i] = (1 - f[2]) * v0 + f[2] * v1;
-  grad[3 * i + 2] = (v1 - v0) * g.res_inv;
-  grad[3 * i + 1] = ((1 - f[2]) * (v10 - v00) + f[2] * (v11 - v01)) * g.res_inv;
+  grad[2] = (v1 - v0) * g.res_inv;
+  grad[1] = ((1 - f[2]) * (v10 - v00) + f[2] * (v11 - v01)) * g.res_inv;
   double g0 = (1 - f[2]) * (1 - f[1]) * (c[1][0][0] - c[0][0][0]);
   g0 += (1 - f[2]) * f[1] * (c[1][1][0] - c[0][1][0]);
   g0 += f[2] * (1 - f[1]) * (c[1][0][1] - c[0][0][1]);
   g0 += f[2] * f[1] * (c[1][1][1] - c[0][1][1]);
   g0 *= g.res_inv;
-  grad[3 * i] = g0;
+  grad[0] = g0;
+  return (1 - f[2]) * v0 + f[2] * v1;
+}
+
+// mode 0: GetDistance(Vector3d)  (ESDFMap.cpp:467-475)      out[i]
+// mode 1: GetDistWithGradTrilinear (ESDFMap.cpp:481-540)    out[i], grad[3i..]
+// mode 2: GetOccupancy(Vector3d)  (ESDFMap.cpp:452-460)      out[i] = 0/1/-10000
+__global__ void k_query(FbGeom g, const uint32_t *cobs, const double *occ, double l_occ, const double *pos, long long n, int mode,
+                        double *out, double *grad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double p[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+  if (mode == 0) { out[i] = fb_query_distance(g, cobs, p); return; }
+  if (mode == 2) {
+    if (!fb_pos_in_map(g, p)) { out[i] = (double)FIESTA_UNDEFINED; return; }
+    const int x = (int)floor((p[0] - g.origin[0]) / g.res), y = (int)floor((p[1] - g.origin[1]) / g.res), z = (int)floor((p[2] - g.origin[2]) / g.res);
+    out[i] = fb_in_grid(g, x, y, z) ? (occ[fb_ii(g, x, y, z)] > l_occ ? 1.0 : 0.0) : 0.0;
+    return;
+  }
+  double gr[3];
+  out[i] = fb_query_trilinear(g, cobs, p, gr);
+  grad[3 * i] = gr[0]; grad[3 * i + 1] = gr[1]; grad[3 * i + 2] = gr[2];
 }
 
 // ====================================================================== host helpers
@@ -296,6 +329,7 @@ static int flush_events(fiesta_map *m) {
 static inline int stage_event(fiesta_map *m, const int *v, int occ) {
   if (m->n_ev == m->cap_ev) { int r = flush_events(m); if (r) return r; }
   const long long ii = fb_ii(m->g, v[0], v[1], v[2]);
+  m->pending_obs = true;
   m->h_ev[m->n_ev++] = (uint32_t)ii | ((uint32_t)occ << 31);
   return FIESTA_OK;
 }
@@ -313,9 +347,11 @@ extern "C" {
 
 const char *fiesta_last_error(void) { return g_last_error.c_str(); }
 
+void fiesta_host_mirror_destroy(struct fiesta_host_mirror *p);
 void fiesta_destroy(fiesta_map *m) {
   if (!m) return;
   cudaSetDevice(m->device);
+  if (m->mirror) fiesta_host_mirror_destroy(m->mirror);                   // a mirror still attached goes with its map
   if (m->stream) cudaStreamSynchronize(m->stream);
   void *dev[] = {m->cobs, m->cobs_b, m->stamp[0], m->stamp[1], m->occbits, m->occ, m->cnt, m->tile_flag, m->nb_flag, m->list[0], m->list[1],
                  m->changed[0], m->changed[1], m->changed_bbox[0], m->changed_bbox[1], m->touch_flag, m->touch_list, m->ins, m->del, m->d_ctr, m->d_ev,
@@ -484,6 +520,7 @@ int fiesta_set_occupancy_batch_vox_device(fiesta_map *m, const int *d_vox, const
   if (m->mode != FIESTA_MODE_FAST) { set_error("fiesta_set_occupancy_batch_vox_device: FAST mode only (device events carry no serial order)"); return FIESTA_ERR_INVALID; }
   if (n == 0) return FIESTA_OK;
   CK(cudaSetDevice(m->device));
+  m->pending_obs = true;
   FbTouch t = {m->cnt, m->touch_flag, m->touch_list, m->touch_epoch, m->d_ctr, nullptr, nullptr};
   k_apply_vox_events<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->g, d_vox, d_occ, n, t);
   m->st.kernel_launches++;
@@ -500,6 +537,7 @@ int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, co
   m->st.rays_cast = m->st.rays_dropped = m->st.ray_voxels = m->st.raycast_rounds = 0; m->st.ms_raycast = 0;
   { int fr = flush_events(m); if (fr) return fr; }                         // per-call SetOccupancy events issued before this frame come first in occupancy_queue_
   if (n == 0) return FIESTA_OK;
+  m->pending_obs = true;
   const FbGeom &g = m->g;
   FbRayArgs a;
   memset(&a, 0, sizeof(a));
@@ -648,6 +686,8 @@ int fiesta_update_occupancy(fiesta_map *m, int global_map) {
   if (!m->params_set) { set_error("fiesta_update_occupancy: SetParameters was never called"); return -FIESTA_ERR_INVALID; }
   if (cudaSetDevice(m->device) != cudaSuccess) return -FIESTA_ERR_CUDA;
   int r;
+  mark_dirty(m);
+  m->pending_obs = false;
   cudaEventRecord(m->ev[0], m->stream);
   if ((r = flush_events(m))) return -r;
   if ((r = fetch_counters(m))) return -r;
@@ -697,6 +737,11 @@ int fiesta_update_esdf(fiesta_map *m) {
   m->st.voxels_changed = m->st.voxels_reset = m->st.tile_visits = m->st.generations = m->st.expansions = 0;
   m->st.ms_update_esdf = m->st.ms_esdf_delete_scan = m->st.ms_esdf_wavefront = 0;
   if (m->n_ins == 0 && m->n_del == 0) return FIESTA_OK;
+  mark_dirty(m);
+  if (m->n_del) {                                                          // dependants of a deleted obstacle are reset wherever they lie,
+    m->dirty_lo[0] = m->dirty_lo[1] = m->dirty_lo[2] = 0;                   // also outside the update box (ESDFMap.cpp:301-334)
+    m->dirty_hi[0] = m->g.gx - 1; m->dirty_hi[1] = m->g.gy - 1; m->dirty_hi[2] = m->g.gz - 1;
+  }
   if (m->mode == FIESTA_MODE_EXACT) {
     FbExactStats xs;
     int launches = 0;
@@ -756,6 +801,7 @@ int fiesta_update_esdf(fiesta_map *m) {
 
 int fiesta_set_update_range(fiesta_map *m, const double min_pos[3], const double max_pos[3], int new_vec) {
   if (!m || !min_pos || !max_pos) return FIESTA_ERR_INVALID;
+  if (m->pending_obs) mark_dirty(m);                                      // observations counted under the old box are integrated later
   FbGeom &g = m->g;
   double lo[3], hi[3];
   for (int i = 0; i < 3; ++i) {                                           // ESDFMap.cpp:794-800
@@ -771,6 +817,7 @@ int fiesta_set_update_range(fiesta_map *m, const double min_pos[3], const double
 }
 int fiesta_set_original_range(fiesta_map *m) {
   if (!m) return FIESTA_ERR_INVALID;
+  if (m->pending_obs) mark_dirty(m);
   FbGeom &g = m->g;
   for (int i = 0; i < 3; ++i) g.min_vec[i] = g.last_min_vec[i] = 0;
   g.max_vec[0] = g.last_max_vec[0] = g.gx - 1; g.max_vec[1] = g.last_max_vec[1] = g.gy - 1; g.max_vec[2] = g.last_max_vec[2] = g.gz - 1;
@@ -906,6 +953,154 @@ int fiesta_query_plan_run(fiesta_query_plan *p) {
   return FIESTA_OK;
 }
 
+// ---- pinned host mirror of the distance records: planners that call GetDistance / GetDistWithGradTrilinear one
+// position at a time (ESDFMap.cpp:467-540) read page-locked host memory instead of paying a device round trip per call.  The
+// mirror holds the packed 4-byte records in the device layout; a refresh diffs the dirty box against a device-side shadow of what
+// the host already has, ships only the changed (index, record) pairs and patches them in.  Every record is one aligned 32-bit
+// word, so a reader racing a refresh sees the old or the new record of a voxel, never a torn one.
+struct fiesta_host_mirror {
+  fiesta_map *m;
+  uint32_t *h_rec;                // pinned [ptotal]
+  uint32_t *d_shadow;             // device [ptotal]: the records the host holds
+  uint2 *d_chg, *h_chg;           // change list, device + pinned
+  size_t cap_chg;
+  unsigned *d_n, *h_n;
+  int64_t last_changed, last_scanned, refreshes, full_copies;
+};
+__global__ void k_mirror_diff(FbGeom g, const uint32_t *cobs, uint32_t *shadow, int lx, int ly, int lz, int ex, int ey, int ez, uint2 *chg,
+                              unsigned cap, unsigned *n) {
+  const long long vol = (long long)ex * ey * ez;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < vol; t += (long long)gridDim.x * blockDim.x) {
+    const int z = lz + (int)(t % ez), y = ly + (int)(t / ez % ey), x = lx + (int)(t / ((long long)ez * ey));
+    const long long ii = fb_ii(g, x, y, z);
+    const uint32_t c = cobs[ii];
+    const bool diff = c != shadow[ii];
+    if (diff) shadow[ii] = c;
+    const unsigned slot = fb_warp_append(n, diff);
+    if (diff && slot < cap) chg[slot] = make_uint2((unsigned)ii, c);      // on overflow the host falls back to one full copy
+  }
+}
+void fiesta_host_mirror_destroy(fiesta_host_mirror *p) {
+  if (!p) return;
+  cudaSetDevice(p->m->device);
+  cudaStreamSynchronize(p->m->stream);
+  if (p->m->mirror == p) p->m->mirror = nullptr;
+  if (p->h_rec) cudaFreeHost(p->h_rec);
+  if (p->h_chg) cudaFreeHost(p->h_chg);
+  if (p->h_n) cudaFreeHost(p->h_n);
+  if (p->d_shadow) cudaFree(p->d_shadow);
+  if (p->d_chg) cudaFree(p->d_chg);
+  if (p->d_n) cudaFree(p->d_n);
+  delete p;
+}
+static int mirror_full_copy(fiesta_host_mirror *p) {
+  fiesta_map *m = p->m;
+  const size_t P = (size_t)m->g.ptotal;
+  CK(cudaMemcpyAsync(p->d_shadow, m->cobs, P * 4, cudaMemcpyDeviceToDevice, m->stream));
+  CK(cudaMemcpyAsync(p->h_rec, m->cobs, P * 4, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  p->full_copies++;
+  return FIESTA_OK;
+}
+int fiesta_host_mirror_create(fiesta_map *m, fiesta_host_mirror **out) {
+  if (!m || !out) { set_error("fiesta_host_mirror_create: null argument"); return FIESTA_ERR_INVALID; }
+  *out = nullptr;
+  if (m->mirror) { set_error("fiesta_host_mirror_create: this map already has a host mirror"); return FIESTA_ERR_INVALID; }
+  CK(cudaSetDevice(m->device));
+  fiesta_host_mirror *p = new (std::nothrow) fiesta_host_mirror();
+  if (!p) return FIESTA_ERR_INVALID;
+  memset((void *)p, 0, sizeof(*p));
+  p->m = m;
+  const size_t P = (size_t)m->g.ptotal;
+  p->cap_chg = P / 32 > (1u << 20) ? P / 32 : (1u << 20);
+  if (p->cap_chg > P) p->cap_chg = P;
+  if (const char *e = getenv("FIESTA_MIRROR_CAP")) { const long v = atol(e); if (v > 0 && (size_t)v < p->cap_chg) p->cap_chg = (size_t)v; }   // tests: force the bulk-copy path
+#define CKP(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s failed: %s", #call, cudaGetErrorString(e__)); fiesta_host_mirror_destroy(p); return FIESTA_ERR_CUDA; } } while (0)
+  CKP(cudaMallocHost((void **)&p->h_rec, P * 4));
+  CKP(cudaMallocHost((void **)&p->h_chg, p->cap_chg * sizeof(uint2)));
+  CKP(cudaMallocHost((void **)&p->h_n, 4));
+  CKP(cudaMalloc((void **)&p->d_shadow, P * 4));
+  CKP(cudaMalloc((void **)&p->d_chg, p->cap_chg * sizeof(uint2)));
+  CKP(cudaMalloc((void **)&p->d_n, 4));
+#undef CKP
+  int r = flush_events(m);
+  if (!r) r = mirror_full_copy(p);
+  if (r) { fiesta_host_mirror_destroy(p); return r; }
+  p->full_copies = 0;
+  m->mirror = p;                                                          // the dirty box is kept: the first refresh rescans it
+  *out = p;
+  return FIESTA_OK;
+}
+int fiesta_host_mirror_refresh(fiesta_host_mirror *p, int64_t *n_changed) {
+  if (!p) return FIESTA_ERR_INVALID;
+  fiesta_map *m = p->m;
+  CK(cudaSetDevice(m->device));
+  p->last_changed = p->last_scanned = 0;
+  p->refreshes++;
+  if (n_changed) *n_changed = 0;
+  if (!m->dirty_any) return FIESTA_OK;
+  const FbGeom &g = m->g;
+  int lo[3], ex[3];
+  const int gs[3] = {g.gx, g.gy, g.gz};
+  bool empty = false;
+  for (int i = 0; i < 3; ++i) {
+    lo[i] = m->dirty_lo[i] < 0 ? 0 : m->dirty_lo[i];
+    const int hi = m->dirty_hi[i] > gs[i] - 1 ? gs[i] - 1 : m->dirty_hi[i];
+    ex[i] = hi - lo[i] + 1;
+    if (ex[i] <= 0) empty = true;
+  }
+  m->dirty_any = false;
+  if (empty) return FIESTA_OK;
+  const long long vol = (long long)ex[0] * ex[1] * ex[2];
+  p->last_scanned = vol;
+  CK(cudaMemsetAsync(p->d_n, 0, 4, m->stream));
+  const long long want = (vol + 255) / 256;
+  const unsigned blocks = (unsigned)(want < 148ll * 16 ? want : 148ll * 16);
+  k_mirror_diff<<<blocks, 256, 0, m->stream>>>(g, m->cobs, p->d_shadow, lo[0], lo[1], lo[2], ex[0], ex[1], ex[2], p->d_chg, (unsigned)p->cap_chg, p->d_n);
+  m->st.kernel_launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(p->h_n, p->d_n, 4, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  const size_t n = *p->h_n;
+  p->last_changed = (int64_t)n;
+  if (n_changed) *n_changed = (int64_t)n;
+  if (n == 0) return FIESTA_OK;
+  if (n > p->cap_chg) return mirror_full_copy(p);                         // the shadow is already current; one bulk copy brings the host up
+  CK(cudaMemcpyAsync(p->h_chg, p->d_chg, n * sizeof(uint2), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  for (size_t i = 0; i < n; ++i) {
+    volatile uint32_t *dst = p->h_rec + p->h_chg[i].x;                     // one aligned 32-bit store per record
+    *dst = p->h_chg[i].y;
+  }
+  return FIESTA_OK;
+}
+double fiesta_host_mirror_get_distance_pos(const fiesta_host_mirror *p, const double pos[3]) {
+  return p ? fb_query_distance(p->m->g, p->h_rec, pos) : (double)FIESTA_UNDEFINED;
+}
+double fiesta_host_mirror_get_distance_vox(const fiesta_host_mirror *p, const int vox[3]) {
+  return p ? fb_get_distance_vox(p->m->g, p->h_rec, vox[0], vox[1], vox[2]) : (double)FIESTA_INFINITY;
+}
+double fiesta_host_mirror_get_dist_grad_trilinear(const fiesta_host_mirror *p, const double pos[3], double grad[3]) {
+  if (!p) { grad[0] = grad[1] = grad[2] = 0; return -1.0; }
+  return fb_query_trilinear(p->m->g, p->h_rec, pos, grad);
+}
+int fiesta_host_mirror_get_distance_batch_pos(const fiesta_host_mirror *p, const double *pos, int64_t n, double *out) {
+  if (!p || (n > 0 && (!pos || !out))) return FIESTA_ERR_INVALID;
+  for (int64_t i = 0; i < n; ++i) out[i] = fb_query_distance(p->m->g, p->h_rec, pos + 3 * i);
+  return FIESTA_OK;
+}
+int fiesta_host_mirror_get_dist_grad_trilinear_batch(const fiesta_host_mirror *p, const double *pos, int64_t n, double *out, double *grad) {
+  if (!p || (n > 0 && (!pos || !out || !grad))) return FIESTA_ERR_INVALID;
+  for (int64_t i = 0; i < n; ++i) out[i] = fb_query_trilinear(p->m->g, p->h_rec, pos + 3 * i, grad + 3 * i);
+  return FIESTA_OK;
+}
+const uint32_t *fiesta_host_mirror_records(const fiesta_host_mirror *p) { return p ? p->h_rec : nullptr; }
+int fiesta_host_mirror_stats(const fiesta_host_mirror *p, int64_t out[4]) {
+  if (!p || !out) return FIESTA_ERR_INVALID;
+  out[0] = p->last_changed; out[1] = p->last_scanned; out[2] = p->refreshes; out[3] = p->full_copies;
+  return FIESTA_OK;
+}
+
 // ---- exports
 static int run_export(fiesta_map *m, double *dist, int *cobs3, double *occ, int *hit, int *tot) {
   CK(cudaSetDevice(m->device));
@@ -979,6 +1174,7 @@ int fiesta_shard_pack(fiesta_map *m, uint32_t *d_lo, uint32_t *d_hi) {
 int fiesta_shard_ingest(fiesta_map *m, const uint32_t *d_from_lo, const uint32_t *d_from_hi, int64_t *changed) {
   if (!m || !changed) return FIESTA_ERR_INVALID;
   CK(cudaSetDevice(m->device));
+  mark_dirty(m);
   FbEsdfArgs a; fill_esdf_args(m, a);
   const int x0 = m->tile_x_lo * 8, x1 = m->tile_x_hi * 8 < m->g.gx ? m->tile_x_hi * 8 : m->g.gx;
   CK(cudaMemsetAsync(m->d_halo_changed, 0, 4, m->stream));
@@ -993,6 +1189,7 @@ int fiesta_shard_ingest(fiesta_map *m, const uint32_t *d_from_lo, const uint32_t
 int fiesta_shard_relax(fiesta_map *m, int64_t *changed) {
   if (!m || !changed) return FIESTA_ERR_INVALID;
   CK(cudaSetDevice(m->device));
+  mark_dirty(m);
   FbEsdfArgs a; fill_esdf_args(m, a);
   k_reset_esdf_ctr<<<1, 1, 0, m->stream>>>(m->d_ctr);
   CK(fb_esdf_wavefront(m->g, a, m->tmap, m->wf_blocks, m->stream));

@@ -174,6 +174,31 @@ const double *fiesta_query_plan_distances(const fiesta_query_plan *p);
 const double *fiesta_query_plan_gradients(const fiesta_query_plan *p);
 int fiesta_query_plan_run(fiesta_query_plan *p);
 
+/* Pinned host mirror of the distance field: for consumers that call GetDistance / GetDistWithGradTrilinear
+ * (ESDFMap.cpp:467-540) one position at a time from host code, where a device round trip per call would dominate.  The mirror
+ * keeps the packed 4-byte distance records (obstacle coordinate per voxel) of the whole grid in page-locked host memory;
+ * fiesta_host_mirror_refresh() -- call it after UpdateESDF -- compares the union of the update boxes used since the previous
+ * refresh with a device-side shadow of what the host holds, copies only the changed (index, record) pairs and patches them in
+ * (more changes than grid/32: one bulk copy).  The getters are pure host code (no CUDA call, no lock) and return the same bits
+ * as fiesta_get_distance_pos / _vox / fiesta_get_dist_grad_trilinear would for the map as of the last refresh.  A record is one
+ * aligned 32-bit word, so a reader running concurrently with a refresh sees a voxel's old or new value, never a mixture.
+ * One mirror per map; costs 4 bytes per voxel of pinned host memory and 4 of device memory.  Destroy it before the map (a
+ * mirror still attached is destroyed with its map). */
+typedef struct fiesta_host_mirror fiesta_host_mirror;
+int fiesta_host_mirror_create(fiesta_map *m, fiesta_host_mirror **out);
+void fiesta_host_mirror_destroy(fiesta_host_mirror *p);
+int fiesta_host_mirror_refresh(fiesta_host_mirror *p, int64_t *n_changed);   /* n_changed (may be NULL): records patched */
+double fiesta_host_mirror_get_distance_pos(const fiesta_host_mirror *p, const double pos[3]);
+double fiesta_host_mirror_get_distance_vox(const fiesta_host_mirror *p, const int vox[3]);
+double fiesta_host_mirror_get_dist_grad_trilinear(const fiesta_host_mirror *p, const double pos[3], double grad[3]);
+int fiesta_host_mirror_get_distance_batch_pos(const fiesta_host_mirror *p, const double *pos_xyz, int64_t n, double *out_dist);
+int fiesta_host_mirror_get_dist_grad_trilinear_batch(const fiesta_host_mirror *p, const double *pos_xyz, int64_t n,
+                                                     double *out_dist, double *out_grad_xyz);
+/* the pinned records themselves (device layout: index = (x*Gy + y)*Pz + z, Pz = Gz rounded up as fiesta_create reports) and
+ * {records patched by the last refresh, voxels it scanned, refreshes so far, bulk copies so far} */
+const uint32_t *fiesta_host_mirror_records(const fiesta_host_mirror *p);
+int fiesta_host_mirror_stats(const fiesta_host_mirror *p, int64_t out[4]);
+
 /* ---- state dumps in the reference's own representation (parity harness; host pointers, grid_total_size entries) ---- */
 int fiesta_export_distance(fiesta_map *m, double *out);             /* distance_buffer_: -10000 unknown, +10000 unreached */
 int fiesta_export_closest_obstacle(fiesta_map *m, int *out_xyz);    /* closest_obstacle_: 3 ints, -10000 = none */

@@ -125,6 +125,16 @@ class ESDFMap {
     return p;
   }
 
+  // Per-call host consumers: a pinned host mirror of the distance records (fiesta_host_mirror_* in fiesta_b200.h).  Call
+  // fiesta_host_mirror_refresh(p, nullptr) after UpdateESDF(); fiesta_host_mirror_get_distance_pos /
+  // fiesta_host_mirror_get_dist_grad_trilinear then answer from host memory with the bits GetDistance /
+  // GetDistWithGradTrilinear return.
+  fiesta_host_mirror *MakeHostMirror() {
+    fiesta_host_mirror *p = nullptr;
+    check(fiesta_host_mirror_create(h_, &p), "MakeHostMirror");
+    return p;
+  }
+
   // ---- visualisation (ESDFMap.h:144-145): flag pass + ordered stream compaction on the device, only the selected points
   // cross PCIe (fiesta_get_point_cloud / fiesta_get_slice_marker) ----
   void GetPointCloud(sensor_msgs::PointCloud &m, int vis_lower_bound, int vis_upper_bound) {

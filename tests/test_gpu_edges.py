@@ -183,3 +183,65 @@ def test_device_resident_event_batch(oracle_built):
         # 20 % random occupancy is the regime where wave propagation (reference and FAST alike) is no longer an exact EDT and the
         # two make different choices at a handful of voxels; occupancy and counters stay identical
         assert r["occ"] == 0 and r["dist"] <= 1e-3 * r["finite"] and r["dist_max_err"] < 0.11, (f, r)
+
+
+@pytest.mark.parametrize("mode,cap", [("exact", None), ("fast", None), ("exact", "64")])
+def test_host_mirror_tracks_every_update(oracle_built, mode, cap, monkeypatch):
+    """fiesta_host_mirror_* (SURVEY.md 8(f) #3): the pinned host records, patched with the changed entries after every update,
+    answer GetDistance / GetDistWithGradTrilinear (ESDFMap.cpp:467-540) from host memory with the bits of the device queries --
+    whole field and random positions, global and sliding local boxes, and through the bulk-copy path (change list of 64)."""
+    if cap:
+        monkeypatch.setenv("FIESTA_MIRROR_CAP", cap)
+    dev, ora = pair(oracle_built, mode, params=scenes.PARAMS_TOGGLE)
+    gs = dev.grid_size
+    allv = scenes.all_voxels(gs)
+    centres = (allv + 0.5) * 0.1 + np.array([-3.2, -3.2, -1.6])
+    rng = np.random.default_rng(11)
+    mir = dev.HostMirror()                                       # created on the empty map: everything unknown
+    assert mir.refresh() == 0
+
+    def check(tag):
+        D = dev.export_distance()
+        want = np.where(D < 0, 10000.0, D)                       # GetDistance reads unknown as +infinity_ (:478)
+        assert np.array_equal(mir.GetDistanceBatch(centres), want), tag
+        q = rng.uniform(-3.4, 3.4, (512, 3)) * (1, 1, 0.5)
+        d1, g1 = dev.GetDistWithGradTrilinearBatch(q)
+        d2, g2 = mir.GetDistWithGradTrilinearBatch(q)
+        assert np.array_equal(d1, d2) and np.array_equal(g1, g2), tag
+        assert np.array_equal(dev.GetDistanceBatch(q), mir.GetDistanceBatch(q)), tag
+        if mode == "exact":                                      # and the reference's own answers where they are defined
+            assert np.array_equal(mir.GetDistanceBatch(centres), ora.GetDistanceBatch(centres)), tag
+
+    for m in (dev, ora):
+        m.SetOccupancyBatchVox(allv, np.zeros(len(allv), np.uint8)); m.UpdateOccupancy(True); m.UpdateESDF()
+    n = mir.refresh()
+    assert n == len(allv) and mir.stats()["full_copies"] == (1 if cap else 0)
+    check("observed")
+    idx = rng.choice(len(allv), 200, replace=False)
+    for m in (dev, ora):
+        m.SetOccupancyBatchVox(allv[idx], np.ones(200, np.uint8)); m.UpdateOccupancy(True); m.UpdateESDF()
+    assert mir.refresh() == len(allv)                            # every voxel got its first finite distance
+    check("obstacles")
+    for r in range(6):                                           # sliding local boxes, inserts and deletes
+        c = np.array([-1.5 + 0.5 * r, -1.0 + 0.3 * r, 0.0])
+        lo, hi = c - np.array([1.1, 1.0, 0.8]), c + np.array([1.1, 1.0, 0.8])
+        vox = np.stack([rng.integers(0, gs[i], 3000) for i in range(3)], -1).astype(np.int32)
+        occ = (rng.random(3000) < (1.0 if r < 3 else 0.4)).astype(np.uint8)       # rounds 0-2 only insert
+        for m in (dev, ora):
+            m.SetUpdateRange(lo, hi)
+            m.SetOccupancyBatchVox(vox, occ); m.UpdateOccupancy(True); m.UpdateESDF()
+        deletes = dev.stats()["deletes"]
+        n = mir.refresh()
+        st = mir.stats()
+        assert st["changed"] == n and 0 < n < st["scanned"], (r, st)
+        # inserts change records inside the update box only; a delete resets dependants anywhere (ESDFMap.cpp:301-334)
+        assert (st["scanned"] == len(allv)) if deletes else (st["scanned"] < len(allv) // 2), (r, st, deletes)
+        check(("box", r))
+    assert mir.refresh() == 0 and mir.stats()["scanned"] == 0    # nothing happened since: nothing is scanned
+    p = (0.31, -0.27, 0.12)
+    assert mir.GetDistance(p) == dev.GetDistance(p)
+    assert mir.GetDistance((10, 20, 5)) == dev.GetDistance((10, 20, 5))
+    d1, g1 = mir.GetDistWithGradTrilinear(p); d2, g2 = dev.GetDistWithGradTrilinear(p)
+    assert d1 == d2 and tuple(g1) == tuple(g2)
+    assert mir.GetDistance((9.0, 0.0, 0.0)) == -10000 and mir.GetDistWithGradTrilinear((9.0, 0.0, 0.0))[0] == -1
+    mir.close()
