@@ -4,6 +4,7 @@
 // compacted IN PIXEL ORDER (the order defines the ray indices of the serial ray casting that follows) and handed to the
 // ray-casting kernels without leaving HBM: one 0.6 MB image goes up instead of a 3.7 MB cloud.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include "../../include/fiesta_b200.h"
 #include "fb_common.cuh"
 
@@ -46,7 +47,7 @@ cudaError_t fb_depth_to_cloud(const uint16_t *d_img, const uint16_t *d_last, int
                               void **tmp, size_t *tmp_bytes, unsigned *h_n, cudaStream_t s) {
   const size_t N = (size_t)rows * cols;
   k_depth_project<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(d_img, d_last, rows, cols, p, filter_on, rel, d_pts, d_flags);
-  cub::CountingInputIterator<uint32_t> it(0);
+  thrust::counting_iterator<uint32_t> it(0);
   size_t bytes = 0;
   cudaError_t e = cub::DeviceSelect::Flagged(nullptr, bytes, it, d_flags, d_sel, d_count, (int)N, s);
   if (e) return e;

@@ -26,12 +26,6 @@
 #define XNONE 0xffffffffu
 #define XMB_NONE 0xffffffffffffffffull
 
-static __constant__ int x_dirs[24][3] = {
-    {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
-    {-1, -1, 0}, {1, 1, 0}, {0, -1, -1}, {0, 1, 1}, {-1, 0, -1}, {1, 0, 1},
-    {-1, 1, 0}, {1, -1, 0}, {0, -1, 1}, {0, 1, -1}, {1, 0, -1}, {-1, 0, 1},
-    {-2, 0, 0}, {2, 0, 0}, {0, -2, 0}, {0, 2, 0}, {0, 0, -2}, {0, 0, 2}};
-
 __device__ __forceinline__ void x_coords(const FbGeom &g, uint32_t ii, int &x, int &y, int &z) {
   z = ii % (unsigned)g.pz; const unsigned xy = ii / (unsigned)g.pz; y = xy % (unsigned)g.gy; x = xy / (unsigned)g.gy;
 }
@@ -42,42 +36,48 @@ __device__ __forceinline__ unsigned x_d2(int x, int y, int z, uint32_t c) {
 __device__ __forceinline__ unsigned x_dist_of(int x, int y, int z, uint32_t c) { return c < 2u ? 0xffffffffu : x_d2(x, y, z, c); }
 
 // ------------------------------------------------------------------ occupancy (ordered)
-__global__ void k_x_gather_keys(const uint32_t *vox, unsigned n, const unsigned long long *tkey, unsigned long long *keys) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) keys[i] = tkey[vox[i]];
-}
-
-// ESDFMap::UpdateOccupancy (ESDFMap.cpp:235-271) over the queue in first-observation order; flags mark insert / delete pushes.
+// ESDFMap::UpdateOccupancy (ESDFMap.cpp:235-271).  What happens to a voxel does not depend on its place in occupancy_queue_;
+// only the ORDER of the insert_queue_ / delete_queue_ pushes does (:263-267).  So the touched voxels are integrated in
+// whatever order they were listed, and the few that cross the occupancy threshold are emitted with their first-observation
+// time and sorted afterwards (hundreds per LIDAR frame, against ~10^6 touched voxels).
 __global__ void k_x_integrate(FbGeom g, const uint32_t *vox, unsigned n, unsigned long long *cnt, double *occ, uint32_t *cobs,
-                              uint32_t *occbits, unsigned long long *tkey, uint8_t *f_ins, uint8_t *f_del, int global_map, double l_hit,
+                              uint32_t *occbits, unsigned long long *tkey, unsigned long long *ins_key, uint32_t *ins_vox,
+                              unsigned long long *del_key, uint32_t *del_vox, unsigned *counts, int global_map, double l_hit,
                               double l_miss, double l_min, double l_max, double l_occ) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t ii = vox[i];
-  uint8_t pi = 0, pd = 0;
-  const unsigned long long c = cnt[ii];
-  const long long hit = (long long)(c >> 32), tot = (long long)(c & 0xffffffffull);
-  cnt[ii] = 0ull;
-  tkey[ii] = ~0ull;
-  const double upd = (hit >= tot - hit) ? l_hit : l_miss;
-  if (cobs[ii] == FB_UNKNOWN) cobs[ii] = FB_INF;
-  double o = occ[ii];
-  const bool was = o > l_occ;
-  const bool skip = (upd >= 0 && o >= l_max) || (upd <= 0 && o <= l_min);
-  if (!skip) {
-    if (!global_map) {                                          // local map (:256-259): occupancy 0, distance_ +infinity_, closest obstacle KEPT
-      int x, y, z; x_coords(g, ii, x, y, z);
-      if (!fb_in_last_range(g, x, y, z)) { o = 0; if ((cobs[ii] & FB_CODE_MASK) >= 2u) cobs[ii] |= FB_DINF; }
+  bool pi = false, pd = false;
+  uint32_t ii = 0;
+  unsigned long long key = 0;
+  if (i < n) {
+    ii = vox[i];
+    const unsigned long long c = cnt[ii];
+    const long long hit = (long long)(c >> 32), tot = (long long)(c & 0xffffffffull);
+    cnt[ii] = 0ull;
+    key = tkey[ii];
+    tkey[ii] = ~0ull;
+    const double upd = (hit >= tot - hit) ? l_hit : l_miss;
+    if (cobs[ii] == FB_UNKNOWN) cobs[ii] = FB_INF;
+    double o = occ[ii];
+    const bool was = o > l_occ;
+    const bool skip = (upd >= 0 && o >= l_max) || (upd <= 0 && o <= l_min);
+    if (!skip) {
+      if (!global_map) {                                        // local map (:256-259): occupancy 0, distance_ +infinity_, closest obstacle KEPT
+        int x, y, z; x_coords(g, ii, x, y, z);
+        if (!fb_in_last_range(g, x, y, z)) { o = 0; if ((cobs[ii] & FB_CODE_MASK) >= 2u) cobs[ii] |= FB_DINF; }
+      }
+      double s = o + upd;
+      s = s > l_min ? s : l_min;
+      s = s < l_max ? s : l_max;
+      occ[ii] = s;
+      const bool now = s > l_occ;
+      if (now && !was) { pi = true; atomicOr(&occbits[ii >> 5], 1u << (ii & 31)); }
+      else if (!now && was) { pd = true; atomicAnd(&occbits[ii >> 5], ~(1u << (ii & 31))); }
     }
-    double s = o + upd;
-    s = s > l_min ? s : l_min;
-    s = s < l_max ? s : l_max;
-    occ[ii] = s;
-    const bool now = s > l_occ;
-    if (now && !was) { pi = 1; atomicOr(&occbits[ii >> 5], 1u << (ii & 31)); }
-    else if (!now && was) { pd = 1; atomicAnd(&occbits[ii >> 5], ~(1u << (ii & 31))); }
   }
-  f_ins[i] = pi; f_del[i] = pd;
+  const unsigned si = fb_warp_append(&counts[0], pi);
+  if (pi) { ins_key[si] = key; ins_vox[si] = ii; }
+  const unsigned sd = fb_warp_append(&counts[1], pd);
+  if (pd) { del_key[sd] = key; del_vox[sd] = ii; }
 }
 
 // ------------------------------------------------------------------ E1: insert seeds
@@ -122,6 +122,10 @@ __global__ void k_x_scan_deps(FbGeom g, const uint32_t *cobs, const uint32_t *ra
     const unsigned slot = fb_warp_append(ndep, dep);
     if (dep && slot < cap) { k1[slot] = r; k2[slot] = ~LS[v]; dv[slot] = (uint32_t)v; }   // ~LS: most recently linked first
   }
+}
+__global__ void k_x_unset(const uint32_t *list, unsigned n, uint32_t *scratch) {   // undo sparse writes: scratch stays all-XNONE between uses
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) scratch[list[i]] = XNONE;
 }
 __global__ void k_x_iota(uint32_t *a, unsigned n) { const unsigned i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = i; }
 __global__ void k_x_gather64(const unsigned long long *src, const uint32_t *idx, unsigned n, unsigned long long *dst) {
@@ -232,7 +236,8 @@ void fb_exact_free(FbExact *X) {
   memset(X, 0, sizeof(*X));
 }
 
-// UpdateOccupancy in first-observation order.  touched[0..n) = voxels with pending observations (any order).
+// UpdateOccupancy; touched[0..n) = voxels with pending observations (any order).  The insert / delete pushes come out in
+// first-observation order = the order in which the reference's occupancy_queue_ would have produced them.
 cudaError_t fb_exact_update_occupancy(FbExact *X, const FbGeom &g, unsigned n, unsigned long long *cnt, double *occ, uint32_t *cobs, uint32_t *occbits,
                                       uint32_t **ins, size_t *cap_ins, unsigned *n_ins, uint32_t **del, size_t *cap_del, unsigned *n_del,
                                       int global_map, const double L[5], cudaStream_t s, int *launches) {
@@ -240,33 +245,31 @@ cudaError_t fb_exact_update_occupancy(FbExact *X, const FbGeom &g, unsigned n, u
   cudaError_t e;
   if ((e = x_ensure(X, &X->k1, &X->cap_k1, n))) return e;
   if ((e = x_ensure(X, &X->k1b, &X->cap_k1b, n))) return e;
+  if ((e = x_ensure(X, &X->k2, &X->cap_k2, n))) return e;
+  if ((e = x_ensure(X, &X->k2b, &X->cap_k2b, n))) return e;
   if ((e = x_ensure(X, &X->deps, &X->cap_deps, n))) return e;
-  if ((e = x_ensure(X, &X->flags, &X->cap_flags, n))) return e;
-  if ((e = x_ensure(X, &X->flags2, &X->cap_flags2, n))) return e;
-  k_x_gather_keys<<<nblk(n), 256, 0, s>>>(X->touched, n, X->tkey, X->k1);
-  if ((e = x_sort_pairs(X, X->k1, X->k1b, X->touched, X->deps, n, s))) return e;
-  k_x_integrate<<<nblk(n), 256, 0, s>>>(g, X->deps, n, cnt, occ, cobs, occbits, X->tkey, X->flags, X->flags2, global_map, L[0], L[1], L[2], L[3], L[4]);
-  *launches += 3;
-  // append to the queues, order kept
-  {   // grow the queues if needed (contents kept)
-    for (int q = 0; q < 2; ++q) {
-      uint32_t **lst = q ? del : ins; size_t *cap = q ? cap_del : cap_ins; const unsigned have = q ? *n_del : *n_ins;
-      if ((size_t)have + n > *cap) {
-        size_t nc = (size_t)have + n + ((size_t)have + n) / 2 + 4096;
-        uint32_t *np = nullptr;
-        XCK(cudaMalloc((void **)&np, nc * 4));
-        if (*lst && have) XCK(cudaMemcpyAsync(np, *lst, (size_t)have * 4, cudaMemcpyDeviceToDevice, s));
-        XCK(cudaStreamSynchronize(s));
-        if (*lst) cudaFree(*lst);
-        *lst = np; *cap = nc;
-      }
+  if ((e = x_ensure(X, &X->dv, &X->cap_dv, n))) return e;
+  XCK(cudaMemsetAsync(X->d_count, 0, 8, s));
+  k_x_integrate<<<nblk(n), 256, 0, s>>>(g, X->touched, n, cnt, occ, cobs, occbits, X->tkey, X->k1, X->deps, X->k2, X->dv, X->d_count, global_map,
+                                        L[0], L[1], L[2], L[3], L[4]);
+  *launches += 1;
+  XCK(cudaMemcpyAsync(X->h_count, X->d_count, 8, cudaMemcpyDeviceToHost, s));
+  XCK(cudaStreamSynchronize(s));
+  const unsigned ni = X->h_count[0], nd = X->h_count[1];
+  for (int q = 0; q < 2; ++q) {                                 // grow the queues if needed (contents kept)
+    uint32_t **lst = q ? del : ins; size_t *cap = q ? cap_del : cap_ins; const unsigned have = q ? *n_del : *n_ins, add = q ? nd : ni;
+    if ((size_t)have + add > *cap) {
+      size_t nc = (size_t)have + add + ((size_t)have + add) / 2 + 4096;
+      uint32_t *np = nullptr;
+      XCK(cudaMalloc((void **)&np, nc * 4));
+      if (*lst && have) XCK(cudaMemcpyAsync(np, *lst, (size_t)have * 4, cudaMemcpyDeviceToDevice, s));
+      XCK(cudaStreamSynchronize(s));
+      if (*lst) cudaFree(*lst);
+      *lst = np; *cap = nc;
     }
   }
-  unsigned c = 0;
-  if ((e = x_select(X, X->deps, X->flags, *ins + *n_ins, n, &c, s))) return e;
-  *n_ins += c;
-  if ((e = x_select(X, X->deps, X->flags2, *del + *n_del, n, &c, s))) return e;
-  *n_del += c;
+  if (ni) { if ((e = x_sort_pairs(X, X->k1, X->k1b, X->deps, *ins + *n_ins, ni, s))) return e; *n_ins += ni; *launches += 1; }
+  if (nd) { if ((e = x_sort_pairs(X, X->k2, X->k2b, X->dv, *del + *n_del, nd, s))) return e; *n_del += nd; *launches += 1; }
   return cudaSuccess;
 }
 
@@ -283,6 +286,7 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
   // ---- E1: insert seeds in insert_queue_ order (:278-291)
   unsigned nE = 0, ndep_run = 0;
   unsigned long long ls_deps = 0;
+  bool scratch_ok = X->scratch_clean;
   if (n_ins) {
     k_x_flag_exist<<<nblk(n_ins), 256, 0, s>>>(ins, n_ins, occ, l_occ, X->flags, 1);
     if ((e = x_select(X, ins, X->flags, X->E[0], n_ins, &nE, s))) return e;
@@ -293,14 +297,18 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
   // ---- E2: deletes (:292-337)
   if (n_del) {
     if ((e = x_ensure(X, &X->sel, &X->cap_sel, (size_t)n_del + 16))) return e;
-    k_x_fill32<<<148 * 8, 256, 0, s>>>(scratch, P, XNONE);
+    // `scratch` (one word per voxel) is all-XNONE between uses: every sparse use below undoes its own writes instead of
+    // refilling 4 bytes per voxel of the grid three times per call
+    if (!X->scratch_clean) { k_x_fill32<<<148 * 8, 256, 0, s>>>(scratch, P, XNONE); *launches += 1; }
+    scratch_ok = true;
+    X->scratch_clean = false;                                  // until the undo kernels below are queued (an error return leaves it false)
     k_x_del_minpos<<<nblk(n_del), 256, 0, s>>>(del, n_del, occ, l_occ, scratch);
     k_x_del_flag<<<nblk(n_del), 256, 0, s>>>(del, n_del, occ, l_occ, scratch, X->flags);
     unsigned nd = 0;
     if ((e = x_select(X, del, X->flags, X->sel, n_del, &nd, s))) return e;
+    k_x_unset<<<nblk(n_del), 256, 0, s>>>(del, n_del, scratch);
     *launches += 3;
     if (nd) {
-      k_x_fill32<<<148 * 8, 256, 0, s>>>(scratch, P, XNONE);
       k_x_del_rank<<<nblk(nd), 256, 0, s>>>(X->sel, nd, scratch);
       // dependants: the list is sized by a first counting attempt, then (rarely) re-run with more room
       unsigned ndep = 0;
@@ -318,6 +326,7 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
         if ((e = x_ensure(X, &X->k2, &X->cap_k2, ndep))) return e;
       }
       st->dependants = ndep;
+      k_x_unset<<<nblk(nd), 256, 0, s>>>(X->sel, nd, scratch);
       if (ndep) {
         if ((e = x_ensure(X, &X->k1b, &X->cap_k1b, ndep))) return e;
         if ((e = x_ensure(X, &X->k2b, &X->cap_k2b, ndep))) return e;
@@ -333,7 +342,6 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
         k_x_gather64<<<nblk(ndep), 256, 0, s>>>(X->k1, X->idx[1], ndep, X->k1b);
         if ((e = x_sort_pairs(X, X->k1b, X->k2b, X->idx[1], X->idx[0], ndep, s))) return e;
         k_x_gather32<<<nblk(ndep), 256, 0, s>>>(X->dv, X->idx[0], ndep, X->deps);
-        k_x_fill32<<<148 * 8, 256, 0, s>>>(scratch, P, XNONE);
         if ((e = x_ensure(X, &X->flags2, &X->cap_flags2, ndep))) return e;
         k_x_set_ord<<<nblk(ndep), 256, 0, s>>>(X->deps, ndep, scratch, X->nc[0], X->flags2);
         *launches += 8;
@@ -356,6 +364,7 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
     h->gen_id = X->gen_id; h->wclock = X->wclock; h->tclock = X->tclock; h->sclock = X->sclock;
     XCK(cudaMemcpyAsync(X->d_ctl, h, sizeof(FbXCtl), cudaMemcpyHostToDevice, s));
     XCK(fb_xrelax_launch(X, g, cobs, nE, X->deps, ndep_run, scratch, X->nc[0], X->flags2, occbits, ls_deps, xdbg ? X->d_dbg : nullptr, s));
+    if (ndep_run) k_x_unset<<<nblk(ndep_run), 256, 0, s>>>(X->deps, ndep_run, scratch);
     XCK(cudaMemcpyAsync(h, X->d_ctl, sizeof(FbXCtl), cudaMemcpyDeviceToHost, s));
     XCK(cudaStreamSynchronize(s));
     *launches += 1;
@@ -377,5 +386,6 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
       fprintf(stderr, "\n");
     }
   }
+  X->scratch_clean = scratch_ok;                             // every sparse write above has its undo queued behind it
   return cudaSuccess;
 }

@@ -32,6 +32,7 @@ struct FbExact {
   unsigned long long tclock;   // relink clock
   unsigned long long key_base; // observation clock
   unsigned *d_count, *d_flag, *h_count;
+  bool scratch_clean;           // the per-voxel scratch word array of UpdateESDF is all-XNONE
   uint4 *SUM;                  // per voxel offer summary of the current generation: {first ts, best ts, best code, snapshot code}
   uint32_t *SUMg;              // per voxel: summary pass for which SUM was computed (each target is claimed once per pass)
   unsigned gen_id, wclock, sclock;

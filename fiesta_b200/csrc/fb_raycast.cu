@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_ray_resolve(FbGeom g, FbRayAr
   cg::grid_group grid = cg::this_grid();
   const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   const unsigned gw = blockIdx.x * RR_WARPS + wib, nwarps = gridDim.x * RR_WARPS;
-  const unsigned gt = blockIdx.x * RR_THREADS + threadIdx.x, nthreads = gridDim.x * RR_THREADS;
+  const unsigned gt = blockIdx.x * RR_THREADS + threadIdx.x;
   const uint32_t *claims = a.stamp[0];
 
   // Event-driven rounds, one grid barrier each.  Round 1 walks every ray.  In a later round each lane looks at one ray and

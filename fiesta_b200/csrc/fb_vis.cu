@@ -3,6 +3,7 @@
 // ESDFMap::GetSliceMarker + RainbowColorMap (:584-699) with a flag pass + ordered stream compaction (CUB), so only the
 // selected points cross PCIe.  Output order = the reference's loop order (x, then y, then z = increasing linear index).
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include "../../include/fiesta_b200.h"
 #include "fb_common.cuh"
 
@@ -70,7 +71,7 @@ static cudaError_t vis_select(const uint8_t *flags, size_t n, uint32_t *sel, uns
   unsigned *d_cnt = nullptr; void *tmp = nullptr; size_t bytes = 0;
   cudaError_t e = cudaMalloc((void **)&d_cnt, 4);
   if (e) return e;
-  cub::CountingInputIterator<uint32_t> it(0);
+  thrust::counting_iterator<uint32_t> it(0);
   e = cub::DeviceSelect::Flagged(nullptr, bytes, it, flags, sel, d_cnt, (int)n, s);
   if (!e) e = cudaMalloc(&tmp, bytes ? bytes : 16);
   if (!e) e = cub::DeviceSelect::Flagged(tmp, bytes, it, flags, sel, d_cnt, (int)n, s);
