@@ -68,7 +68,7 @@ struct FbGeom {
 struct FbCounters {
   unsigned n_touched, n_ins, n_del;   // n_touched: voxels integrated by the last UpdateOccupancy
   unsigned n_touch_tiles;      // tiles holding pending observations (the occupancy queue)
-  unsigned n_xtouched;         // exact mode: voxels holding pending observations
+  unsigned pad_x0;
   unsigned n_list[2];          // active-tile work lists (ping-pong)
   unsigned n_changed[2];       // changed-tile lists by generation parity
   unsigned next_work[4];       // dynamic tile fetch counters: [phase1 even, phase1 odd, phase2 even, phase2 odd]
@@ -125,22 +125,22 @@ struct FbTouch {
   uint32_t *touch_flag, *touch_list;
   unsigned epoch;
   FbCounters *ctr;
-  unsigned long long *tkey;   // exact mode only (else nullptr): per-voxel serial time of the first pending observation
-  uint32_t *xtouched;         // exact mode only: voxels with pending observations
+  unsigned long long *tkey;   // exact mode only (else nullptr): per-voxel serial time of the first pending observation, epoch-coded
+  unsigned long long key_hi;  // exact mode: integration epoch << FB_KEY_BITS
 };
+// Exact mode: tkey[v] = (epoch << 44) | (2^44-1 - t), t = serial time of an observation within the current integration epoch
+// (the observations between two UpdateOccupancy calls).  atomicMax keeps the EARLIEST observation of the NEWEST epoch, so the
+// array is never reset: entries of older epochs simply lose.
+#define FB_KEY_BITS 44
+#define FB_KEY_MASK ((1ull << FB_KEY_BITS) - 1ull)
 // One observation of voxel ii (ESDFMap.cpp:424-435): num_miss_++, num_hit_ += occ; the first one since the last
-// integration (num_miss_ == 1) queues the voxel -- fast mode: marks its 8^3 tile; exact mode: lists the voxel and keeps
-// the serial time `key` of its earliest observation (= its position in occupancy_queue_).
+// integration (num_miss_ == 1) queues the voxel.  The queue is kept per 8^3 tile: a tile is queued when it holds any pending
+// observation, which is the same set as "some voxel of it saw its first observation" -- so the counter update needs no return
+// value (a fire-and-forget RED instead of a round trip).  Exact mode additionally keeps the serial time `key` of the voxel's
+// earliest pending observation (= its position in occupancy_queue_) with one more RED.
 __device__ __forceinline__ void fb_touch(const FbGeom &g, const FbTouch &t, unsigned ii, unsigned occ, unsigned long long key) {
-  if (t.tkey) {
-    const unsigned long long old = atomicAdd(&t.cnt[ii], ((unsigned long long)occ << 32) | 1ull);
-    atomicMin(&t.tkey[ii], key);
-    if ((unsigned)(old & 0xffffffffull) == 0u) t.xtouched[atomicAdd(&t.ctr->n_xtouched, 1u)] = ii;
-    return;
-  }
-  // Fast mode: the tile is queued when it holds any pending observation, which is the same set as "some voxel of it saw its
-  // first observation" -- so the counter update needs no return value (a fire-and-forget RED instead of a round trip).
   atomicAdd(&t.cnt[ii], ((unsigned long long)occ << 32) | 1ull);
+  if (t.tkey) atomicMax(&t.tkey[ii], t.key_hi | (FB_KEY_MASK - (key < FB_KEY_MASK ? key : FB_KEY_MASK)));
   const unsigned z = ii % (unsigned)g.pz, xy = ii / (unsigned)g.pz, y = xy % (unsigned)g.gy, x = xy / (unsigned)g.gy;
   const unsigned tile = ((x >> 3) * g.ty + (y >> 3)) * g.tz + (z >> 3);
   if (__ldcg(&t.touch_flag[tile]) != t.epoch && atomicExch(&t.touch_flag[tile], t.epoch) != t.epoch)
@@ -179,8 +179,8 @@ struct FbRayArgs {
   uint32_t *touch_flag, *touch_list;
   unsigned touch_epoch;
   unsigned long long *tkey;   // exact mode (else nullptr)
-  uint32_t *xtouched;
-  unsigned long long key_base;
+  unsigned long long key_hi;  // exact mode: integration epoch << FB_KEY_BITS
+  unsigned long long key_base;  // serial time of this frame's first observation within the epoch
   uint32_t *ray_list;     // [n][cap] row-major, reversed (t = 0 is the voxel before the last emitted one)
   int *ray_len, *ray_reach;
   unsigned *ray_dirty;    // lowest list position a lower ray displaced this ray from since its last walk (FB_RAY_CLEAN: none)

@@ -35,51 +35,6 @@ __device__ __forceinline__ unsigned x_d2(int x, int y, int z, uint32_t c) {
 }
 __device__ __forceinline__ unsigned x_dist_of(int x, int y, int z, uint32_t c) { return c < 2u ? 0xffffffffu : x_d2(x, y, z, c); }
 
-// ------------------------------------------------------------------ occupancy (ordered)
-// ESDFMap::UpdateOccupancy (ESDFMap.cpp:235-271).  What happens to a voxel does not depend on its place in occupancy_queue_;
-// only the ORDER of the insert_queue_ / delete_queue_ pushes does (:263-267).  So the touched voxels are integrated in
-// whatever order they were listed, and the few that cross the occupancy threshold are emitted with their first-observation
-// time and sorted afterwards (hundreds per LIDAR frame, against ~10^6 touched voxels).
-__global__ void k_x_integrate(FbGeom g, const uint32_t *vox, unsigned n, unsigned long long *cnt, double *occ, uint32_t *cobs,
-                              uint32_t *occbits, unsigned long long *tkey, unsigned long long *ins_key, uint32_t *ins_vox,
-                              unsigned long long *del_key, uint32_t *del_vox, unsigned *counts, int global_map, double l_hit,
-                              double l_miss, double l_min, double l_max, double l_occ) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool pi = false, pd = false;
-  uint32_t ii = 0;
-  unsigned long long key = 0;
-  if (i < n) {
-    ii = vox[i];
-    const unsigned long long c = cnt[ii];
-    const long long hit = (long long)(c >> 32), tot = (long long)(c & 0xffffffffull);
-    cnt[ii] = 0ull;
-    key = tkey[ii];
-    tkey[ii] = ~0ull;
-    const double upd = (hit >= tot - hit) ? l_hit : l_miss;
-    if (cobs[ii] == FB_UNKNOWN) cobs[ii] = FB_INF;
-    double o = occ[ii];
-    const bool was = o > l_occ;
-    const bool skip = (upd >= 0 && o >= l_max) || (upd <= 0 && o <= l_min);
-    if (!skip) {
-      if (!global_map) {                                        // local map (:256-259): occupancy 0, distance_ +infinity_, closest obstacle KEPT
-        int x, y, z; x_coords(g, ii, x, y, z);
-        if (!fb_in_last_range(g, x, y, z)) { o = 0; if ((cobs[ii] & FB_CODE_MASK) >= 2u) cobs[ii] |= FB_DINF; }
-      }
-      double s = o + upd;
-      s = s > l_min ? s : l_min;
-      s = s < l_max ? s : l_max;
-      occ[ii] = s;
-      const bool now = s > l_occ;
-      if (now && !was) { pi = true; atomicOr(&occbits[ii >> 5], 1u << (ii & 31)); }
-      else if (!now && was) { pd = true; atomicAnd(&occbits[ii >> 5], ~(1u << (ii & 31))); }
-    }
-  }
-  const unsigned si = fb_warp_append(&counts[0], pi);
-  if (pi) { ins_key[si] = key; ins_vox[si] = ii; }
-  const unsigned sd = fb_warp_append(&counts[1], pd);
-  if (pd) { del_key[sd] = key; del_vox[sd] = ii; }
-}
-
 // ------------------------------------------------------------------ E1: insert seeds
 __global__ void k_x_flag_exist(const uint32_t *list, unsigned n, const double *occ, double l_occ, uint8_t *flags, int want) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -179,11 +134,12 @@ static cudaError_t x_select(FbExact *X, const uint32_t *in, const uint8_t *flags
   *count = *X->h_count;
   return cudaSuccess;
 }
-static cudaError_t x_sort_pairs(FbExact *X, const unsigned long long *kin, unsigned long long *kout, const uint32_t *vin, uint32_t *vout, unsigned n, cudaStream_t s) {
+static cudaError_t x_sort_pairs(FbExact *X, const unsigned long long *kin, unsigned long long *kout, const uint32_t *vin, uint32_t *vout, unsigned n, cudaStream_t s,
+                                int key_bits = 64) {
   size_t bytes = 0;
-  XCK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, 64, s));
+  XCK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, key_bits, s));
   cudaError_t e = x_tmp(X, bytes); if (e) return e;
-  XCK(cub::DeviceRadixSort::SortPairs(X->cub_tmp, bytes, kin, kout, vin, vout, (int)n, 0, 64, s));
+  XCK(cub::DeviceRadixSort::SortPairs(X->cub_tmp, bytes, kin, kout, vin, vout, (int)n, 0, key_bits, s));
   return cudaSuccess;
 }
 cudaError_t fb_exact_init(FbExact *X, const FbGeom &g, int device, cudaStream_t s) {
@@ -221,9 +177,9 @@ cudaError_t fb_exact_init(FbExact *X, const FbGeom &g, int device, cudaStream_t 
   XCK(cudaMallocHost((void **)&X->h_count, 16));
   XCK(cudaMemsetAsync(X->d_count, 0, 16, s)); XCK(cudaMemsetAsync(X->d_flag, 0, 16, s));
   k_x_fill64<<<148 * 8, 256, 0, s>>>(X->MB, P, XMB_NONE);
-  k_x_fill64<<<148 * 8, 256, 0, s>>>(X->tkey, P, ~0ull);
+  XCK(cudaMemsetAsync(X->tkey, 0, P * 8, s));
   XCK(cudaMemsetAsync(X->LS, 0, P * 8, s));
-  X->tclock = 1; X->key_base = 0; X->gen_id = 0; X->wclock = 0; X->sclock = 0;
+  X->tclock = 1; X->key_base = 0; X->key_epoch = 1; X->key_hi = 1ull << FB_KEY_BITS; X->gen_id = 0; X->wclock = 0; X->sclock = 0;
   return cudaGetLastError();
 }
 void fb_exact_free(FbExact *X) {
@@ -236,23 +192,13 @@ void fb_exact_free(FbExact *X) {
   memset(X, 0, sizeof(*X));
 }
 
-// UpdateOccupancy; touched[0..n) = voxels with pending observations (any order).  The insert / delete pushes come out in
-// first-observation order = the order in which the reference's occupancy_queue_ would have produced them.
-cudaError_t fb_exact_update_occupancy(FbExact *X, const FbGeom &g, unsigned n, unsigned long long *cnt, double *occ, uint32_t *cobs, uint32_t *occbits,
-                                      uint32_t **ins, size_t *cap_ins, unsigned *n_ins, uint32_t **del, size_t *cap_del, unsigned *n_del,
-                                      int global_map, const double L[5], cudaStream_t s, int *launches) {
-  if (n == 0) return cudaSuccess;
+// Second half of UpdateOccupancy (ESDFMap.cpp:263-267): k_integrate<true> (fb_map.cu) staged the voxels that crossed the
+// occupancy threshold with the serial time of their first observation; sorted by that time they are appended to
+// insert_queue_ / delete_queue_ in the order the reference's walk over occupancy_queue_ pushes them.
+cudaError_t fb_exact_queue_crossings(FbExact *X, const unsigned long long *ins_key, const uint32_t *ins_vox, const unsigned long long *del_key,
+                                     const uint32_t *del_vox, uint32_t **ins, size_t *cap_ins, unsigned *n_ins, uint32_t **del, size_t *cap_del,
+                                     unsigned *n_del, cudaStream_t s, int *launches) {
   cudaError_t e;
-  if ((e = x_ensure(X, &X->k1, &X->cap_k1, n))) return e;
-  if ((e = x_ensure(X, &X->k1b, &X->cap_k1b, n))) return e;
-  if ((e = x_ensure(X, &X->k2, &X->cap_k2, n))) return e;
-  if ((e = x_ensure(X, &X->k2b, &X->cap_k2b, n))) return e;
-  if ((e = x_ensure(X, &X->deps, &X->cap_deps, n))) return e;
-  if ((e = x_ensure(X, &X->dv, &X->cap_dv, n))) return e;
-  XCK(cudaMemsetAsync(X->d_count, 0, 8, s));
-  k_x_integrate<<<nblk(n), 256, 0, s>>>(g, X->touched, n, cnt, occ, cobs, occbits, X->tkey, X->k1, X->deps, X->k2, X->dv, X->d_count, global_map,
-                                        L[0], L[1], L[2], L[3], L[4]);
-  *launches += 1;
   XCK(cudaMemcpyAsync(X->h_count, X->d_count, 8, cudaMemcpyDeviceToHost, s));
   XCK(cudaStreamSynchronize(s));
   const unsigned ni = X->h_count[0], nd = X->h_count[1];
@@ -268,8 +214,19 @@ cudaError_t fb_exact_update_occupancy(FbExact *X, const FbGeom &g, unsigned n, u
       *lst = np; *cap = nc;
     }
   }
-  if (ni) { if ((e = x_sort_pairs(X, X->k1, X->k1b, X->deps, *ins + *n_ins, ni, s))) return e; *n_ins += ni; *launches += 1; }
-  if (nd) { if ((e = x_sort_pairs(X, X->k2, X->k2b, X->dv, *del + *n_del, nd, s))) return e; *n_del += nd; *launches += 1; }
+  if ((e = x_ensure(X, &X->k1b, &X->cap_k1b, ni > nd ? ni : nd))) return e;
+  if (ni) { if ((e = x_sort_pairs(X, ins_key, X->k1b, ins_vox, *ins + *n_ins, ni, s, FB_KEY_BITS))) return e; *n_ins += ni; *launches += 1; }
+  if (nd) { if ((e = x_sort_pairs(X, del_key, X->k1b, del_vox, *del + *n_del, nd, s, FB_KEY_BITS))) return e; *n_del += nd; *launches += 1; }
+  return cudaSuccess;
+}
+// A new integration epoch: later observations beat everything recorded so far in tkey (fb_touch), so nothing is reset.
+cudaError_t fb_exact_next_epoch(FbExact *X, const FbGeom &g, cudaStream_t s) {
+  X->key_base = 0;
+  if (++X->key_epoch >= (1u << (64 - FB_KEY_BITS))) {          // epoch field exhausted (2^20 integrations): start over on a zeroed array
+    XCK(cudaMemsetAsync(X->tkey, 0, (size_t)g.ptotal * 8, s));
+    X->key_epoch = 1;
+  }
+  X->key_hi = (unsigned long long)X->key_epoch << FB_KEY_BITS;
   return cudaSuccess;
 }
 

@@ -27,10 +27,12 @@ struct FbXCtl {
 struct FbExact {
   unsigned long long *MB;      // per voxel: {parity | queue position | behaviour | code} of its live entry in the current generation
   unsigned long long *LS;      // per voxel: time of the last relink into a dependant list
-  unsigned long long *tkey;    // per voxel: serial time of the first pending observation
-  uint32_t *touched;           // voxels with pending observations (unordered; ordered by tkey at integration)
+  unsigned long long *tkey;    // per voxel: epoch-coded serial time of the first pending observation (fb_touch, fb_common.cuh)
+  uint32_t *touched;           // [ptotal] staging of the voxels whose occupancy crossed the threshold (inserts; deletes use emask)
   unsigned long long tclock;   // relink clock
-  unsigned long long key_base; // observation clock
+  unsigned long long key_base; // observation clock within the current integration epoch
+  unsigned long long key_hi;   // key_epoch << FB_KEY_BITS
+  unsigned key_epoch;          // integration epoch (one per UpdateOccupancy)
   unsigned *d_count, *d_flag, *h_count;
   bool scratch_clean;           // the per-voxel scratch word array of UpdateESDF is all-XNONE
   uint4 *SUM;                  // per voxel offer summary of the current generation: {first ts, best ts, best code, snapshot code}
@@ -56,9 +58,10 @@ struct FbExact {
 
 cudaError_t fb_exact_init(FbExact *X, const FbGeom &g, int device, cudaStream_t s);
 void fb_exact_free(FbExact *X);
-cudaError_t fb_exact_update_occupancy(FbExact *X, const FbGeom &g, unsigned n, unsigned long long *cnt, double *occ, uint32_t *cobs, uint32_t *occbits,
-                                      uint32_t **ins, size_t *cap_ins, unsigned *n_ins, uint32_t **del, size_t *cap_del, unsigned *n_del,
-                                      int global_map, const double L[5], cudaStream_t s, int *launches);
+cudaError_t fb_exact_queue_crossings(FbExact *X, const unsigned long long *ins_key, const uint32_t *ins_vox, const unsigned long long *del_key,
+                                     const uint32_t *del_vox, uint32_t **ins, size_t *cap_ins, unsigned *n_ins, uint32_t **del, size_t *cap_del,
+                                     unsigned *n_del, cudaStream_t s, int *launches);
+cudaError_t fb_exact_next_epoch(FbExact *X, const FbGeom &g, cudaStream_t s);
 cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, uint32_t *scratch, const double *occ, const uint32_t *occbits, double l_occ,
                                  const uint32_t *ins, unsigned n_ins, const uint32_t *del, unsigned n_del, cudaStream_t s, FbExactStats *st, int *launches);
 // fb_xrelax.cu

@@ -66,7 +66,6 @@ struct fiesta_map {
   int shard_rank, shard_world, tile_x_lo, tile_x_hi;
   unsigned *d_halo_changed;
   FbExact X;
-  unsigned n_xtouched;
   fiesta_stats st;
   // pinned host mirror (next #3): union of the update boxes that were current while records could change
   struct fiesta_host_mirror *mirror;
@@ -96,7 +95,7 @@ __global__ void k_reset_esdf_ctr(FbCounters *c) {
 }
 __global__ void k_reset_touched(FbCounters *c) { c->n_touched = 0; }
 __global__ void k_reset_queues(FbCounters *c, int touched, int insdel) {
-  if (touched) { c->n_touch_tiles = 0; c->n_xtouched = 0; }
+  if (touched) c->n_touch_tiles = 0;
   if (insdel) c->n_ins = c->n_del = 0;
 }
 
@@ -120,9 +119,16 @@ __global__ void k_apply_vox_events(FbGeom g, const int *vox, const uint8_t *occ,
 // O2: ESDFMap::UpdateOccupancy (ESDFMap.cpp:235-271).  One 128-thread CTA streams the counters of one queued 8^3 tile
 // (4 voxels = one 32-byte sector per thread); every voxel with pending observations is integrated exactly as the
 // reference does.  Voxels are independent, so the queue order does not matter for the result.
+// EXACT = order-exact mode: only the ORDER of the insert_queue_ / delete_queue_ pushes depends on the voxel's place in
+// occupancy_queue_ (:263-267), so the few voxels that cross the threshold are emitted together with the serial time of their
+// first observation (hundreds per LIDAR frame, against millions of touched voxels) and sorted afterwards; the local-map
+// reset keeps the closest obstacle (flag bit FB_DINF, :256-259).
+template <bool EXACT>
 __global__ void __launch_bounds__(128) k_integrate(FbGeom g, const uint32_t *tiles, unsigned ntiles, unsigned long long *cnt, double *occ,
-                                                   uint32_t *cobs, uint32_t *occbits, uint32_t *ins, uint32_t *del, FbCounters *ctr,
-                                                   int global_map, double l_hit, double l_miss, double l_min, double l_max, double l_occ) {
+                                                   uint32_t *cobs, uint32_t *occbits, uint32_t *ins, uint32_t *del, unsigned *n_ins, unsigned *n_del,
+                                                   FbCounters *ctr, const unsigned long long *tkey, unsigned long long *ins_key,
+                                                   unsigned long long *del_key, int global_map, double l_hit, double l_miss, double l_min,
+                                                   double l_max, double l_occ) {
   const int row = threadIdx.x >> 1, half = threadIdx.x & 1;
   const int lx = row >> 3, ly = row & 7;
   unsigned touched = 0;
@@ -151,7 +157,11 @@ __global__ void __launch_bounds__(128) k_integrate(FbGeom g, const uint32_t *til
         const bool was = o > l_occ;                                         // Exist(idx) before (:242)
         const bool skip = (upd >= 0 && o >= l_max) || (upd <= 0 && o <= l_min);   // already clamped in that direction (:250-255)
         if (!skip) {
-          if (!global_map && !fb_in_last_range(g, x, y, z0 + k)) { o = 0; cobs[ii] = FB_INF; }   // local map (:256-259)
+          if (!global_map && !fb_in_last_range(g, x, y, z0 + k)) {          // local map (:256-259): occupancy 0, distance_ +infinity_
+            o = 0;
+            if (EXACT) { if ((cobs[ii] & FB_CODE_MASK) >= 2u) cobs[ii] |= FB_DINF; }   // ... and the closest obstacle is KEPT
+            else cobs[ii] = FB_INF;
+          }
           double s = o + upd;
           s = s > l_min ? s : l_min;
           s = s < l_max ? s : l_max;
@@ -161,10 +171,10 @@ __global__ void __launch_bounds__(128) k_integrate(FbGeom g, const uint32_t *til
           else if (!now && was) { push_del = true; atomicAnd(&occbits[ii >> 5], ~(1u << (ii & 31))); }  // delete_queue_.push (:265-266)
         }
       }
-      const unsigned si = fb_warp_append(&ctr->n_ins, push_ins);
-      if (push_ins) ins[si] = ii;
-      const unsigned sd = fb_warp_append(&ctr->n_del, push_del);
-      if (push_del) del[sd] = ii;
+      const unsigned si = fb_warp_append(n_ins, push_ins);
+      if (push_ins) { ins[si] = ii; if (EXACT) ins_key[si] = FB_KEY_MASK - (tkey[ii] & FB_KEY_MASK); }
+      const unsigned sd = fb_warp_append(n_del, push_del);
+      if (push_del) { del[sd] = ii; if (EXACT) del_key[sd] = FB_KEY_MASK - (tkey[ii] & FB_KEY_MASK); }
     }
   }
   touched = __reduce_add_sync(0xffffffffu, touched);
@@ -310,14 +320,15 @@ static int ensure(T **ptr, size_t *cap, size_t need, bool keep, cudaStream_t s) 
 static int fetch_counters(fiesta_map *m) {
   CK(cudaMemcpyAsync(m->h_ctr, m->d_ctr, sizeof(FbCounters), cudaMemcpyDeviceToHost, m->stream));
   CK(cudaStreamSynchronize(m->stream));
-  m->n_touch_tiles = m->h_ctr->n_touch_tiles; m->n_xtouched = m->h_ctr->n_xtouched;
+  m->n_touch_tiles = m->h_ctr->n_touch_tiles;
   if (m->mode == FIESTA_MODE_FAST) { m->n_ins = m->h_ctr->n_ins; m->n_del = m->h_ctr->n_del; }
   return FIESTA_OK;
 }
 static int flush_events(fiesta_map *m) {
   if (m->n_ev == 0) return FIESTA_OK;
   CK(cudaMemcpyAsync(m->d_ev, m->h_ev, m->n_ev * sizeof(uint32_t), cudaMemcpyHostToDevice, m->stream));
-  FbTouch t = {m->cnt, m->touch_flag, m->touch_list, m->touch_epoch, m->d_ctr, m->mode == FIESTA_MODE_EXACT ? m->X.tkey : nullptr, m->X.touched};
+  if (m->mode == FIESTA_MODE_EXACT && m->X.key_base + m->n_ev >= FB_KEY_MASK) { set_error("more than 2^44 observations between two UpdateOccupancy calls"); return FIESTA_ERR_LIMIT; }
+  FbTouch t = {m->cnt, m->touch_flag, m->touch_list, m->touch_epoch, m->d_ctr, m->mode == FIESTA_MODE_EXACT ? m->X.tkey : nullptr, m->X.key_hi};
   k_apply_events<<<(unsigned)((m->n_ev + 255) / 256), 256, 0, m->stream>>>(m->g, m->d_ev, m->n_ev, t, m->X.key_base);
   m->X.key_base += m->n_ev;
   m->st.kernel_launches++;
@@ -521,7 +532,7 @@ int fiesta_set_occupancy_batch_vox_device(fiesta_map *m, const int *d_vox, const
   if (n == 0) return FIESTA_OK;
   CK(cudaSetDevice(m->device));
   m->pending_obs = true;
-  FbTouch t = {m->cnt, m->touch_flag, m->touch_list, m->touch_epoch, m->d_ctr, nullptr, nullptr};
+  FbTouch t = {m->cnt, m->touch_flag, m->touch_list, m->touch_epoch, m->d_ctr, nullptr, 0ull};
   k_apply_vox_events<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->g, d_vox, d_occ, n, t);
   m->st.kernel_launches++;
   CK(cudaGetLastError());
@@ -536,6 +547,9 @@ int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, co
   CK(cudaSetDevice(m->device));
   m->st.rays_cast = m->st.rays_dropped = m->st.ray_voxels = m->st.raycast_rounds = 0; m->st.ms_raycast = 0;
   { int fr = flush_events(m); if (fr) return fr; }                         // per-call SetOccupancy events issued before this frame come first in occupancy_queue_
+  if (m->mode == FIESTA_MODE_EXACT && m->X.key_base + (1ull << 30) >= FB_KEY_MASK) {
+    set_error("fiesta_raycast_frame: more than 16383 frames between two UpdateOccupancy calls (order-exact mode)"); return FIESTA_ERR_LIMIT;
+  }
   if (n == 0) return FIESTA_OK;
   m->pending_obs = true;
   const FbGeom &g = m->g;
@@ -596,8 +610,8 @@ int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, co
   if ((r = ensure(&m->ray_list, &m->cap_ray_list, (size_t)a.cap * (size_t)n, false, m->stream))) return r;
   a.cnt = m->cnt; a.stamp[0] = m->stamp[0]; a.stamp[1] = m->stamp[1];
   a.touch_flag = m->touch_flag; a.touch_list = m->touch_list; a.touch_epoch = m->touch_epoch;
-  a.tkey = m->mode == FIESTA_MODE_EXACT ? m->X.tkey : nullptr; a.xtouched = m->X.touched; a.key_base = m->X.key_base;
-  m->X.key_base += 1ull << 30;
+  a.tkey = m->mode == FIESTA_MODE_EXACT ? m->X.tkey : nullptr; a.key_hi = m->X.key_hi; a.key_base = m->X.key_base;
+  m->X.key_base += 1ull << 30;                                            // (point index << 11) + position along the ray < 2^30
   a.ray_list = m->ray_list; a.ray_len = m->ray_len; a.ray_reach = m->ray_reach; a.ray_dirty = m->ray_dirty; a.ctr = m->d_ctr;
   static const bool dbg_ray = getenv("FIESTA_DEBUG_RAY") != nullptr;
   a.dbg = nullptr;
@@ -678,7 +692,7 @@ int fiesta_last_depth_cloud(fiesta_map *m, float *out, int64_t cap, int64_t *n_p
 
 int fiesta_check_update(fiesta_map *m) {
   if (!m) return 0;
-  return (m->n_ev > 0 || m->n_touch_tiles > 0 || m->n_xtouched > 0) ? 1 : 0;                       // !occupancy_queue_.empty(), ESDFMap.cpp:229
+  return (m->n_ev > 0 || m->n_touch_tiles > 0) ? 1 : 0;                       // !occupancy_queue_.empty(), ESDFMap.cpp:229
 }
 
 int fiesta_update_occupancy(fiesta_map *m, int global_map) {
@@ -691,32 +705,42 @@ int fiesta_update_occupancy(fiesta_map *m, int global_map) {
   cudaEventRecord(m->ev[0], m->stream);
   if ((r = flush_events(m))) return -r;
   if ((r = fetch_counters(m))) return -r;
+  const unsigned n = m->n_touch_tiles;
+  m->st.occupancy_updates = 0;
   if (m->mode == FIESTA_MODE_EXACT) {
-    const unsigned nx = m->n_xtouched;
-    m->st.occupancy_updates = nx;
-    if (nx) {
-      const double L[5] = {m->l_hit, m->l_miss, m->l_min, m->l_max, m->l_occ};
-      int launches = 0;
-      if (fb_exact_update_occupancy(&m->X, m->g, nx, m->cnt, m->occ, m->cobs, m->occbits, &m->ins, &m->cap_ins, &m->n_ins, &m->del, &m->cap_del,
-                                    &m->n_del, global_map, L, m->stream, &launches) != cudaSuccess) { set_error("exact UpdateOccupancy: %s", m->X.err); return -FIESTA_ERR_CUDA; }
+    if (n) {
+      FbExact &X = m->X;
+      k_reset_touched<<<1, 1, 0, m->stream>>>(m->d_ctr);
+      cudaMemsetAsync(X.d_count, 0, 8, m->stream);
+      const unsigned blocks = n < 148u * 16u ? n : 148u * 16u;
+      // crossings are staged (voxel, first-observation time) in arrays that are scratch between two k_x_relax launches
+      unsigned long long *ikey = reinterpret_cast<unsigned long long *>(X.SUM), *dkey = ikey + m->g.ptotal;
+      k_integrate<true><<<blocks, 128, 0, m->stream>>>(m->g, m->touch_list, n, m->cnt, m->occ, m->cobs, m->occbits, X.touched, X.emask, X.d_count, X.d_count + 1,
+                                                       m->d_ctr, X.tkey, ikey, dkey, global_map, m->l_hit, m->l_miss, m->l_min, m->l_max, m->l_occ);
       k_reset_queues<<<1, 1, 0, m->stream>>>(m->d_ctr, 1, 0);
-      m->st.kernel_launches += launches + 1;
+      m->touch_epoch++;
+      m->st.kernel_launches += 3;
+      int launches = 0;
+      if (fb_exact_queue_crossings(&X, ikey, X.touched, dkey, X.emask, &m->ins, &m->cap_ins, &m->n_ins, &m->del, &m->cap_del, &m->n_del, m->stream, &launches) != cudaSuccess) {
+        set_error("exact UpdateOccupancy: %s", X.err); return -FIESTA_ERR_CUDA;
+      }
+      m->st.kernel_launches += launches;
+      if ((r = fb_exact_next_epoch(&X, m->g, m->stream))) { set_error("exact UpdateOccupancy: %s", X.err); return -FIESTA_ERR_CUDA; }
     }
     cudaEventRecord(m->ev[1], m->stream);
     if ((r = fetch_counters(m))) return -r;
     cudaEventElapsedTime(&m->st.ms_update_occupancy, m->ev[0], m->ev[1]);
+    if (n) m->st.occupancy_updates = m->h_ctr->n_touched;
     m->st.touched_voxels = 0;
     return (m->n_ins > 0 || m->n_del > 0) ? 1 : 0;
   }
-  const unsigned n = m->n_touch_tiles;
-  m->st.occupancy_updates = 0;
   if (n) {
     if ((r = ensure(&m->ins, &m->cap_ins, (size_t)m->n_ins + (size_t)n * 512, true, m->stream))) return -r;
     if ((r = ensure(&m->del, &m->cap_del, (size_t)m->n_del + (size_t)n * 512, true, m->stream))) return -r;
     k_reset_touched<<<1, 1, 0, m->stream>>>(m->d_ctr);
     const unsigned blocks = n < 148u * 16u ? n : 148u * 16u;
-    k_integrate<<<blocks, 128, 0, m->stream>>>(m->g, m->touch_list, n, m->cnt, m->occ, m->cobs, m->occbits, m->ins, m->del, m->d_ctr,
-                                              global_map, m->l_hit, m->l_miss, m->l_min, m->l_max, m->l_occ);
+    k_integrate<false><<<blocks, 128, 0, m->stream>>>(m->g, m->touch_list, n, m->cnt, m->occ, m->cobs, m->occbits, m->ins, m->del, &m->d_ctr->n_ins, &m->d_ctr->n_del,
+                                                     m->d_ctr, nullptr, nullptr, nullptr, global_map, m->l_hit, m->l_miss, m->l_min, m->l_max, m->l_occ);
     k_reset_queues<<<1, 1, 0, m->stream>>>(m->d_ctr, 1, 0);
     m->touch_epoch++;
     m->st.kernel_launches += 3;

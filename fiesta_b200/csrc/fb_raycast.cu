@@ -84,7 +84,7 @@ __device__ __forceinline__ int fb_endpoint(const FbRayArgs &a, long long i, doub
 // sub = 0 for the endpoint observation of point i, 1 + t for the free-space observation at back-walk position t: the serial
 // reference makes them in exactly this order (Fiesta.h:213-215, then :239-276).
 __device__ __forceinline__ void fb_count(const FbGeom &g, const FbRayArgs &a, long long ii, unsigned occ, unsigned long long i, unsigned sub) {
-  FbTouch t = {a.cnt, a.touch_flag, a.touch_list, a.touch_epoch, a.ctr, a.tkey, a.xtouched};
+  FbTouch t = {a.cnt, a.touch_flag, a.touch_list, a.touch_epoch, a.ctr, a.tkey, a.key_hi};
   fb_touch(g, t, (unsigned)ii, occ, a.key_base + (i << 11) + sub);
 }
 
