@@ -14,8 +14,10 @@
 //    re-seeding ("first valid neighbour in dirs_ order", :308-321, which sees earlier re-seeded dependants) is iterated to
 //    its fixpoint the same way.
 //  * occupancy_queue_ order = order of first observation: every observation carries its serial time (host event number,
-//    or point index and position along the ray); the per-voxel minimum orders the integration, so insert_queue_ /
-//    delete_queue_ come out in the reference's order.
+//    or point index and position along the ray) and the per-voxel earliest one is kept (fb_touch).  The integration of a
+//    voxel does not depend on its place in the queue, only the order of the insert_queue_ / delete_queue_ pushes does:
+//    the tile-streamed k_integrate<true> (fb_map.cu) stages the threshold crossings with that time and
+//    fb_exact_queue_crossings sorts just those, so the queues come out in the reference's order.
 #include <cub/cub.cuh>
 #include <stdio.h>
 #include <stdlib.h>
