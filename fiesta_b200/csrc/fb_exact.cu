@@ -65,8 +65,9 @@ __global__ void k_x_del_rank(const uint32_t *sel, unsigned n, uint32_t *scratch)
   if (i < n) scratch[sel[i]] = i;
 }
 // Dependants = voxels whose closest obstacle is a deleted one (the reference walks head_[idx] -> next_, :301).
+// shift > 0: one combined sort key (rank << shift) | (low `shift` bits of ~LS); shift == 0: two keys for two stable sorts.
 __global__ void k_x_scan_deps(FbGeom g, const uint32_t *cobs, const uint32_t *rank, const unsigned long long *LS, unsigned long long *k1,
-                              unsigned long long *k2, uint32_t *dv, unsigned *ndep, unsigned cap) {
+                              unsigned long long *k2, uint32_t *dv, unsigned *ndep, unsigned cap, int shift) {
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < g.ptotal; v += (long long)gridDim.x * blockDim.x) {
     const uint32_t c = cobs[v] & FB_CODE_MASK;
     bool dep = false;
@@ -77,7 +78,12 @@ __global__ void k_x_scan_deps(FbGeom g, const uint32_t *cobs, const uint32_t *ra
       dep = r != XNONE;
     }
     const unsigned slot = fb_warp_append(ndep, dep);
-    if (dep && slot < cap) { k1[slot] = r; k2[slot] = ~LS[v]; dv[slot] = (uint32_t)v; }   // ~LS: most recently linked first
+    if (dep && slot < cap) {
+      const unsigned long long inv = ~LS[v];                   // ~LS: most recently linked first
+      if (shift) k1[slot] = ((unsigned long long)r << shift) | (inv & ((1ull << shift) - 1ull));
+      else { k1[slot] = r; k2[slot] = inv; }
+      dv[slot] = (uint32_t)v;
+    }
   }
 }
 __global__ void k_x_unset(const uint32_t *list, unsigned n, uint32_t *scratch) {   // undo sparse writes: scratch stays all-XNONE between uses
@@ -269,12 +275,18 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
     *launches += 3;
     if (nd) {
       k_x_del_rank<<<nblk(nd), 256, 0, s>>>(X->sel, nd, scratch);
+      // order of the reference's list walk = (obstacle's position in delete_queue_, link time descending).  Both fit one
+      // 64-bit key as long as (bits of the rank) + (bits of the relink clock) <= 64 -- one radix sort; else two stable sorts
+      int rank_bits = 1; while ((1ull << rank_bits) < (unsigned long long)nd) ++rank_bits;
+      int clock_bits = 1; while (clock_bits < 64 && (X->tclock >> clock_bits)) ++clock_bits;
+      const bool two_sorts = getenv("FIESTA_X_TWO_SORTS") != nullptr;              // tests: force the fallback
+      const int shift = (rank_bits + clock_bits <= 64 && !two_sorts) ? 64 - rank_bits : 0;
       // dependants: the list is sized by a first counting attempt, then (rarely) re-run with more room
       unsigned ndep = 0;
       for (int attempt = 0; attempt < 2; ++attempt) {
         size_t cap = X->cap_dv;
         XCK(cudaMemsetAsync(X->d_count, 0, 4, s));
-        k_x_scan_deps<<<148 * 16, 256, 0, s>>>(g, cobs, scratch, X->LS, X->k1, X->k2, X->dv, X->d_count, (unsigned)((cap < X->cap_k1 ? cap : X->cap_k1) < X->cap_k2 ? (cap < X->cap_k1 ? cap : X->cap_k1) : X->cap_k2));
+        k_x_scan_deps<<<148 * 16, 256, 0, s>>>(g, cobs, scratch, X->LS, X->k1, X->k2, X->dv, X->d_count, (unsigned)((cap < X->cap_k1 ? cap : X->cap_k1) < X->cap_k2 ? (cap < X->cap_k1 ? cap : X->cap_k1) : X->cap_k2), shift);
         XCK(cudaMemcpyAsync(X->h_count, X->d_count, 4, cudaMemcpyDeviceToHost, s));
         XCK(cudaStreamSynchronize(s));
         ndep = *X->h_count;
@@ -295,15 +307,20 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
         if ((e = x_ensure(X, &X->nc[0], &X->cap_nc[0], ndep))) return e;
         if ((e = x_ensure(X, &X->nc[1], &X->cap_nc[1], ndep))) return e;
         if ((e = x_ensure(X, &X->flags, &X->cap_flags, ndep))) return e;
-        // order = (obstacle's position in delete_queue_, link time descending): two stable radix sorts
-        k_x_iota<<<nblk(ndep), 256, 0, s>>>(X->idx[0], ndep);
-        if ((e = x_sort_pairs(X, X->k2, X->k2b, X->idx[0], X->idx[1], ndep, s))) return e;
-        k_x_gather64<<<nblk(ndep), 256, 0, s>>>(X->k1, X->idx[1], ndep, X->k1b);
-        if ((e = x_sort_pairs(X, X->k1b, X->k2b, X->idx[1], X->idx[0], ndep, s))) return e;
-        k_x_gather32<<<nblk(ndep), 256, 0, s>>>(X->dv, X->idx[0], ndep, X->deps);
+        if (shift) {
+          if ((e = x_sort_pairs(X, X->k1, X->k1b, X->dv, X->deps, ndep, s))) return e;
+          *launches += 1;
+        } else {
+          k_x_iota<<<nblk(ndep), 256, 0, s>>>(X->idx[0], ndep);
+          if ((e = x_sort_pairs(X, X->k2, X->k2b, X->idx[0], X->idx[1], ndep, s))) return e;
+          k_x_gather64<<<nblk(ndep), 256, 0, s>>>(X->k1, X->idx[1], ndep, X->k1b);
+          if ((e = x_sort_pairs(X, X->k1b, X->k2b, X->idx[1], X->idx[0], ndep, s))) return e;
+          k_x_gather32<<<nblk(ndep), 256, 0, s>>>(X->dv, X->idx[0], ndep, X->deps);
+          *launches += 5;
+        }
         if ((e = x_ensure(X, &X->flags2, &X->cap_flags2, ndep))) return e;
         k_x_set_ord<<<nblk(ndep), 256, 0, s>>>(X->deps, ndep, scratch, X->nc[0], X->flags2);
-        *launches += 8;
+        *launches += 1;
         ndep_run = ndep; ls_deps = X->tclock;                // the fixpoint and the hand-over to E[0] run inside k_x_relax
         X->tclock += ndep;
       }

@@ -146,9 +146,12 @@ def test_exact_pillar_replay(oracle_built):
         assert_identical(dev, ora, "delete %d" % k)
 
 
-@pytest.mark.parametrize("observed", [1.0, 0.6])
-def test_exact_random_insert_delete(oracle_built, observed):
-    """Mixed insert/delete rounds, fully and partially (salt-and-pepper) observed: the adversarial case for tie-breaks."""
+@pytest.mark.parametrize("observed,two_sorts", [(1.0, False), (0.6, False), (0.6, True)])
+def test_exact_random_insert_delete(oracle_built, observed, two_sorts, monkeypatch):
+    """Mixed insert/delete rounds, fully and partially (salt-and-pepper) observed: the adversarial case for tie-breaks.
+    two_sorts: the dependant order through the two-key fallback (rank and relink clock no longer fit one 64-bit sort key)."""
+    if two_sorts:
+        monkeypatch.setenv("FIESTA_X_TWO_SORTS", "1")
     rng = np.random.default_rng(21)
     dev, ora = make_exact_pair(oracle_built, (-2.0, -2.0, -2.0), 0.1, (3.95, 3.95, 3.15), scenes.PARAMS_TOGGLE)
     gs = dev.grid_size
