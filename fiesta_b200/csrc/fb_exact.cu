@@ -66,16 +66,18 @@ __global__ void k_x_del_rank(const uint32_t *sel, unsigned n, uint32_t *scratch)
 }
 // Dependants = voxels whose closest obstacle is a deleted one (the reference walks head_[idx] -> next_, :301).
 // shift > 0: one combined sort key (rank << shift) | (low `shift` bits of ~LS); shift == 0: two keys for two stable sorts.
-__global__ void k_x_scan_deps(FbGeom g, const uint32_t *cobs, const uint32_t *rank, const unsigned long long *LS, unsigned long long *k1,
-                              unsigned long long *k2, uint32_t *dv, unsigned *ndep, unsigned cap, int shift) {
+__global__ void k_x_scan_deps(FbGeom g, const uint32_t *cobs, const uint32_t *occbits, const uint32_t *rank, const unsigned long long *LS,
+                              unsigned long long *k1, unsigned long long *k2, uint32_t *dv, unsigned *ndep, unsigned cap, int shift) {
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < g.ptotal; v += (long long)gridDim.x * blockDim.x) {
     const uint32_t c = cobs[v] & FB_CODE_MASK;
     bool dep = false;
     unsigned r = 0;
     if (c >= 2u) {
       int ox, oy, oz; fb_unpack(c, ox, oy, oz);
-      r = rank[fb_ii(g, ox, oy, oz)];
-      dep = r != XNONE;
+      const long long oi = fb_ii(g, ox, oy, oz);
+      // a deleted obstacle is no longer occupied: the occupancy bitmap (1 bit per voxel, L2-resident) filters out the voxels
+      // whose obstacle still stands before the random look-up into the per-voxel rank array
+      if (!((__ldg(&occbits[oi >> 5]) >> (oi & 31)) & 1u)) { r = rank[oi]; dep = r != XNONE; }
     }
     const unsigned slot = fb_warp_append(ndep, dep);
     if (dep && slot < cap) {
@@ -286,7 +288,7 @@ cudaError_t fb_exact_update_esdf(FbExact *X, const FbGeom &g, uint32_t *cobs, ui
       for (int attempt = 0; attempt < 2; ++attempt) {
         size_t cap = X->cap_dv;
         XCK(cudaMemsetAsync(X->d_count, 0, 4, s));
-        k_x_scan_deps<<<148 * 16, 256, 0, s>>>(g, cobs, scratch, X->LS, X->k1, X->k2, X->dv, X->d_count, (unsigned)((cap < X->cap_k1 ? cap : X->cap_k1) < X->cap_k2 ? (cap < X->cap_k1 ? cap : X->cap_k1) : X->cap_k2), shift);
+        k_x_scan_deps<<<148 * 16, 256, 0, s>>>(g, cobs, occbits, scratch, X->LS, X->k1, X->k2, X->dv, X->d_count, (unsigned)((cap < X->cap_k1 ? cap : X->cap_k1) < X->cap_k2 ? (cap < X->cap_k1 ? cap : X->cap_k1) : X->cap_k2), shift);
         XCK(cudaMemcpyAsync(X->h_count, X->d_count, 4, cudaMemcpyDeviceToHost, s));
         XCK(cudaStreamSynchronize(s));
         ndep = *X->h_count;

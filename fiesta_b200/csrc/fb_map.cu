@@ -99,6 +99,15 @@ __global__ void k_reset_queues(FbCounters *c, int touched, int insdel) {
   if (insdel) c->n_ins = c->n_del = 0;
 }
 
+// occupancy bitmap = Exist(idx) for every voxel (ESDFMap.cpp:46-48) under a new occupancy threshold
+__global__ void k_rebuild_occbits(const double *occ, long long ptotal, double l_occ, uint32_t *occbits) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w * 32 >= ptotal) return;
+  uint32_t bits = 0;
+  for (int k = 0; k < 32; ++k) { const long long v = w * 32 + k; if (v < ptotal && occ[v] > l_occ) bits |= 1u << k; }
+  occbits[w] = bits;
+}
+
 // O1 counter part for per-call SetOccupancy events staged on the host (ESDFMap.cpp:424-435).
 __global__ void k_apply_events(FbGeom g, const uint32_t *ev, size_t n, FbTouch t, unsigned long long key_base) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -475,8 +484,16 @@ int fiesta_create(const fiesta_config *cfg, fiesta_map **out) {
 
 int fiesta_set_parameters(fiesta_map *m, double p_hit, double p_miss, double p_min, double p_max, double p_occ) {
   if (!m) return FIESTA_ERR_INVALID;
+  const double old_occ = m->l_occ;
   m->l_hit = log(p_hit / (1 - p_hit)); m->l_miss = log(p_miss / (1 - p_miss));     // Logit, ESDFMap.cpp:12-14
   m->l_min = log(p_min / (1 - p_min)); m->l_max = log(p_max / (1 - p_max)); m->l_occ = log(p_occ / (1 - p_occ));
+  if (m->params_set && m->l_occ != old_occ) {                              // Exist() (ESDFMap.cpp:46-48) compares with the CURRENT threshold:
+    CK(cudaSetDevice(m->device));                                         // bring the occupancy bitmap the ESDF kernels read in line with it
+    const size_t words = ((size_t)m->g.ptotal + 31) / 32;
+    k_rebuild_occbits<<<(unsigned)((words + 255) / 256), 256, 0, m->stream>>>(m->occ, m->g.ptotal, m->l_occ, m->occbits);
+    m->st.kernel_launches++;
+    CK(cudaGetLastError());
+  }
   m->params_set = true;
   return FIESTA_OK;
 }

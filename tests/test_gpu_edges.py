@@ -245,3 +245,43 @@ def test_host_mirror_tracks_every_update(oracle_built, mode, cap, monkeypatch):
     assert d1 == d2 and tuple(g1) == tuple(g2)
     assert mir.GetDistance((9.0, 0.0, 0.0)) == -10000 and mir.GetDistWithGradTrilinear((9.0, 0.0, 0.0))[0] == -1
     mir.close()
+
+
+def test_occupancy_threshold_change_exact(oracle_built):
+    """SetParameters with a new p_occ on a map that already holds data (ESDFMap.cpp:218-224): Exist() (:46-48) follows the new
+    threshold at once -- voxels between the two thresholds count as obstacles without ever having been inserted -- and every
+    later delete / re-seeding decision uses it.  Arrays compared with the reference after every update."""
+    dev, ora = pair(oracle_built, "exact")                                  # PARAMS_DEFAULT: two hits make a voxel occupied
+    gs = dev.grid_size
+    allv = scenes.all_voxels(gs)
+    rng = np.random.default_rng(5)
+    pick = rng.choice(len(allv), 900, replace=False)
+    A, B = allv[pick[:500]], allv[pick[500:]]
+
+    def step(vox, occ, tag):
+        for m in (dev, ora):
+            m.SetOccupancyBatchVox(vox, occ)
+        assert dev.UpdateOccupancy(True) == ora.UpdateOccupancy(True), tag
+        dev.UpdateESDF(); ora.UpdateESDF()
+        res = compare(dev, ora)
+        assert res["occ"] == 0 and res["dist"] == 0 and res["cobs_tie"] == 0 and res["cobs_nontie"] == 0, (tag, res)
+        assert dev.stats()["expansions"] == ora.stats()["expansions"], tag
+
+    step(allv, np.zeros(len(allv), np.uint8), "observe")
+    step(np.concatenate([A, B]), np.ones(900, np.uint8), "hit 1")           # log-odds -0.619 + 0.847 = 0.228
+    step(A, np.ones(500, np.uint8), "hit 2")                                # A 1.075: still below logit(0.8) = 1.386
+    step(A, np.ones(500, np.uint8), "hit 3")                                # A 1.92: inserted.  B stays at 0.228 > logit(0.55) = 0.2
+    assert dev.stats()["inserts"] == 500
+    for m in (dev, ora):
+        m.SetParameters(0.70, 0.35, 0.12, 0.97, 0.55)                       # B voxels now Exist() without an insert
+    for r in range(5):
+        n = 1200
+        vox = np.concatenate([A[rng.choice(500, 150, replace=False)], B[rng.choice(400, 150, replace=False)],
+                              np.stack([rng.integers(0, gs[i], n) for i in range(3)], -1).astype(np.int32)])
+        occ = (rng.random(len(vox)) < 0.45).astype(np.uint8)
+        step(vox, occ, ("after threshold change", r))
+    for m in (dev, ora):
+        m.SetParameters(*scenes.PARAMS_DEFAULT)                             # and back up
+    for r in range(3):
+        vox = np.stack([rng.integers(0, gs[i], 1500) for i in range(3)], -1).astype(np.int32)
+        step(vox, (rng.random(1500) < 0.5).astype(np.uint8), ("threshold restored", r))
