@@ -34,6 +34,29 @@ int main() {
   std::printf("trilinear %.9f %.9f %.9f %.9f\n", d, g(0), g(1), g(2));
   std::printf("out_of_map %d %.1f %.1f\n", map->SetOccupancy(Eigen::Vector3d(99, 0, 0), 1), map->GetDistance(Eigen::Vector3d(99, 0, 0)),
               map->GetDistWithGradTrilinear(Eigen::Vector3d(99, 0, 0), g));
+  {   // planner-side additions of the facade: CUDA-graph query plan and pinned host mirror return the same bits as the per-call queries
+    fiesta_query_plan *plan = map->MakeQueryPlan(4);
+    double *qp = fiesta_query_plan_positions(plan);
+    const double pts[4][3] = {{0.33, -1.27, 2.51}, {-3.05, 2.2, 0.71}, {5.9, 5.9, 11.3}, {99, 0, 0}};
+    for (int i = 0; i < 4; ++i) for (int k = 0; k < 3; ++k) qp[3 * i + k] = pts[i][k];
+    fiesta_query_plan_run(plan);
+    fiesta_host_mirror *mir = map->MakeHostMirror();
+    fiesta_host_mirror_refresh(mir, nullptr);
+    int same = 1;
+    for (int i = 0; i < 4; ++i) {
+      Eigen::Vector3d gi(0, 0, 0);
+      const double di = map->GetDistWithGradTrilinear(Eigen::Vector3d(pts[i][0], pts[i][1], pts[i][2]), gi);
+      double gm[3];
+      const double dm = fiesta_host_mirror_get_dist_grad_trilinear(mir, pts[i], gm);
+      const double *gp = fiesta_query_plan_gradients(plan) + 3 * i;
+      same = same && di == fiesta_query_plan_distances(plan)[i] && di == dm;
+      for (int k = 0; k < 3; ++k) same = same && gi(k) == gp[k] && gi(k) == gm[k];
+      same = same && map->GetDistance(Eigen::Vector3d(pts[i][0], pts[i][1], pts[i][2])) == fiesta_host_mirror_get_distance_pos(mir, pts[i]);
+    }
+    std::printf("plan_and_mirror_equal %d\n", same);
+    fiesta_host_mirror_destroy(mir);
+    fiesta_query_plan_destroy(plan);
+  }
   sensor_msgs::PointCloud pc;
   map->GetPointCloud(pc, 0, 63);
   std::printf("occupied_points %zu\n", pc.points.size());

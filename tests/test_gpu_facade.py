@@ -39,5 +39,6 @@ def test_facade_pillar_replay(tmp_path):
     got = [float(x) for x in vals["trilinear"]]
     assert abs(got[0] - t["dist"]) < 1e-9 and all(abs(a - b) < 1e-9 for a, b in zip(got[1:], t["grad"]))
     assert vals["out_of_map"] == ["-10000", "-10000.0", "-1.0"]
+    assert vals["plan_and_mirror_equal"] == ["1"]
     assert int(vals["occupied_points"][0]) == 625
     assert int(vals["slice_points"][0]) == 64 * 64
