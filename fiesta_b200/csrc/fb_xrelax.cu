@@ -51,6 +51,34 @@ static __constant__ int x_dirs[24][3] = {
     {-2, 0, 0}, {2, 0, 0}, {0, -2, 0}, {0, 2, 0}, {0, 0, -2}, {0, 0, 2}};
 static __constant__ int x_off_c[X_NOFF];     // the distinct sums a+b, packed (dx+4) | (dy+4)<<4 | (dz+4)<<8 (filled by fb_xrelax_init)
 
+// Index arithmetic is a third of this kernel's instruction stream (ncu source view, profiles/r02_xrelax_ncu.md): 64-bit linear
+// indices, six-compare box tests and divisions by the run-time pitch.  The forms below are exact for every grid the library
+// accepts (< 2^30 voxels): 32-bit indices, unsigned range tests, multiply-high divisions with host-made constants.
+__device__ __forceinline__ unsigned x_vi(const FbGeom &g, int x, int y, int z) { return (unsigned)((x * g.gy + y) * g.pz + z); }
+__device__ __forceinline__ bool x_in_grid(const FbGeom &g, int x, int y, int z) {
+  return (unsigned)x < (unsigned)g.gx && (unsigned)y < (unsigned)g.gy && (unsigned)z < (unsigned)g.gz;
+}
+// VoxInRange (ESDFMap.cpp:63-72); fb_xrelax_launch makes min_vec / max_vec of the kernel's copy an unreachable box when the
+// update box is empty, so max - min >= 0 here
+__device__ __forceinline__ bool x_in_range(const FbGeom &g, int x, int y, int z) {
+  return (unsigned)(x - g.min_vec[0]) <= (unsigned)(g.max_vec[0] - g.min_vec[0]) && (unsigned)(y - g.min_vec[1]) <= (unsigned)(g.max_vec[1] - g.min_vec[1]) &&
+         (unsigned)(z - g.min_vec[2]) <= (unsigned)(g.max_vec[2] - g.min_vec[2]);
+}
+// dirs_[j][k] for a compile-time j (unrolled loops): folded into immediates, unlike a read of the constant-memory table
+__device__ __forceinline__ int x_dc(int j, int k) {
+  const int D[24][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}, {-1, -1, 0}, {1, 1, 0}, {0, -1, -1}, {0, 1, 1}, {-1, 0, -1}, {1, 0, 1},
+                        {-1, 1, 0}, {1, -1, 0}, {0, -1, 1}, {0, 1, -1}, {1, 0, -1}, {-1, 0, 1}, {-2, 0, 0}, {2, 0, 0}, {0, -2, 0}, {0, 2, 0}, {0, 0, -2}, {0, 0, 2}};
+  return D[j][k];
+}
+// word of the j-th writer of the in-grid voxel v = (x,y,z), i.e. of the entry at (x,y,z) - dirs_[j]: only the components the
+// direction moves need a bounds test, and the linear index is v minus a per-direction constant
+__device__ __forceinline__ unsigned long long x_writer_word(const FbGeom &g, const unsigned long long *MB, unsigned v, int x, int y, int z, int j, bool inr) {
+  const int dx = x_dc(j, 0), dy = x_dc(j, 1), dz = x_dc(j, 2);
+  const bool ok = inr && (dx == 0 || (unsigned)(x - dx) < (unsigned)g.gx) && (dy == 0 || (unsigned)(y - dy) < (unsigned)g.gy) &&
+                  (dz == 0 || (unsigned)(z - dz) < (unsigned)g.gz);
+  return ok ? __ldcg(&MB[v - (unsigned)((dx * g.gy + dy) * g.pz + dz)]) : XMB_NONE;
+}
+
 struct XShared {
   int off[X_NOFF];                    // copy of x_off_c (lane-varying index: shared memory, not the constant cache)
   int dir[32];                        // dirs_ packed the same way; entry 24 = (0,0,0)
@@ -60,9 +88,6 @@ struct XShared {
   unsigned base, total;
 };
 
-__device__ __forceinline__ void x_coords(const FbGeom &g, uint32_t ii, int &x, int &y, int &z) {
-  z = ii % (unsigned)g.pz; const unsigned xy = ii / (unsigned)g.pz; y = xy % (unsigned)g.gy; x = xy / (unsigned)g.gy;
-}
 __device__ __forceinline__ unsigned x_d2(int x, int y, int z, uint32_t c) {
   int ox, oy, oz; fb_unpack(c, ox, oy, oz); ox -= x; oy -= y; oz -= z;
   return (unsigned)(ox * ox + oy * oy + oz * oz);
@@ -87,18 +112,15 @@ template <bool WANT_FIRST>
 __device__ __forceinline__ XState x_gather(const FbGeom &g, const uint32_t *cobs, const unsigned long long *MB, int x, int y, int z, unsigned T,
                                            unsigned &first, uint32_t &snap) {
   XState s;
-  const long long v = fb_ii(g, x, y, z);
+  const unsigned v = x_vi(g, x, y, z);
   // All loads are issued before anything is decided (the round trip to L2 is what a query costs): the snapshot, the own
   // word and the first half of the writers' words together, then the second half.
-  const bool inr = fb_in_range(g, x, y, z);                    // pushes only go to voxels inside the update box (:378)
+  const bool inr = x_in_range(g, x, y, z);                    // pushes only go to voxels inside the update box (:378)
   unsigned long long w[XGB];
   const uint32_t snap_raw = __ldcg(&cobs[v]);
   const unsigned long long wown = __ldcg(&MB[v]);
 #pragma unroll
-  for (int j = 0; j < XGB; ++j) {
-    const int qx = x - x_dirs[j][0], qy = y - x_dirs[j][1], qz = z - x_dirs[j][2];
-    w[j] = (inr && fb_in_grid(g, qx, qy, qz)) ? __ldcg(&MB[fb_ii(g, qx, qy, qz)]) : XMB_NONE;
-  }
+  for (int j = 0; j < XGB; ++j) w[j] = x_writer_word(g, MB, v, x, y, z, j, inr);
   snap = snap_raw & FB_CODE_MASK;
   s.c = snap; s.d = (snap_raw & FB_DINF) ? 0xffffffffu : x_dist_of(x, y, z, s.c); s.ts = XNONE;   // FB_DINF: distance_ forced to +infinity_ (:256-259)
   first = XNONE;
@@ -108,10 +130,7 @@ __device__ __forceinline__ XState x_gather(const FbGeom &g, const uint32_t *cobs
   for (int h = 0; h < 24 / XGB; ++h) {
     if (h >= 1) {
 #pragma unroll
-      for (int j = 0; j < XGB; ++j) {
-        const int qx = x - x_dirs[XGB * h + j][0], qy = y - x_dirs[XGB * h + j][1], qz = z - x_dirs[XGB * h + j][2];
-        w[j] = (inr && fb_in_grid(g, qx, qy, qz)) ? __ldcg(&MB[fb_ii(g, qx, qy, qz)]) : XMB_NONE;
-      }
+      for (int j = 0; j < XGB; ++j) w[j] = x_writer_word(g, MB, v, x, y, z, XGB * h + j, inr);
     }
 #pragma unroll
     for (int j = 0; j < XGB; ++j) {
@@ -141,14 +160,14 @@ __device__ __forceinline__ XState x_gather(const FbGeom &g, const uint32_t *cobs
 __device__ __forceinline__ void x_summarize(const FbGeom &g, const uint32_t *cobs, const unsigned long long *MB, uint4 *SUM, int x, int y, int z) {
   unsigned first; uint32_t snap;
   const XState f = x_gather<true>(g, cobs, MB, x, y, z, XNONE, first, snap);
-  SUM[fb_ii(g, x, y, z)] = make_uint4(first, f.ts, f.c, snap);
+  SUM[x_vi(g, x, y, z)] = make_uint4(first, f.ts, f.c, snap);
 }
 template <bool USE_SUM>
 __device__ __forceinline__ XState x_state(const FbGeom &g, const uint32_t *cobs, const unsigned long long *MB, const uint4 *SUM, int x, int y, int z,
                                           unsigned T, uint32_t &snap) {
   unsigned first;
   if (USE_SUM) {
-    const uint4 u = __ldcg(&SUM[fb_ii(g, x, y, z)]);
+    const uint4 u = __ldcg(&SUM[x_vi(g, x, y, z)]);
     snap = u.w;
     XState s;
     if (u.x == XNONE || T <= u.x) { s.c = u.w; s.d = x_dist_of(x, y, z, s.c); s.ts = XNONE; return s; }
@@ -196,7 +215,17 @@ struct XArgs {
   const uint32_t *occbits;
   unsigned long long ls_deps;   // link time of dependant 0 (InsertIntoList order, :333)
   unsigned long long *dbg;  // optional per-generation trace {nE, rounds, ns} (FIESTA_DEBUG_X)
+  unsigned div_pz_m, div_pz_s, div_gy_m, div_gy_s;   // n / d = umulhi(n, m) >> s for n < 2^31 (x_div_make); m == 0: d == 1
 };
+// voxel index -> coordinates: two divisions by run-time constants, as multiply-high + shift
+__device__ __forceinline__ unsigned x_div(unsigned n, unsigned m, unsigned s) { return m ? (__umulhi(n, m) >> s) : n; }
+__device__ __forceinline__ void x_coords(const XArgs &a, uint32_t ii, int &x, int &y, int &z) {
+  const unsigned xy = x_div(ii, a.div_pz_m, a.div_pz_s);
+  z = (int)(ii - xy * (unsigned)a.g.pz);
+  const unsigned xx = x_div(xy, a.div_gy_m, a.div_gy_s);
+  y = (int)(xy - xx * (unsigned)a.g.gy);
+  x = (int)xx;
+}
 
 __device__ __forceinline__ void x_unpack_off(int o, int &dx, int &dy, int &dz) { dx = (o & 15) - 4; dy = ((o >> 4) & 15) - 4; dz = ((o >> 8) & 15) - 4; }
 
@@ -206,8 +235,8 @@ __device__ __forceinline__ void x_claim_summaries(const XArgs &a, const XShared 
   if (lane >= 25u) return;
   int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
   const int nx = x + dx, ny = y + dy, nz = z + dz;
-  if (!fb_in_grid(a.g, nx, ny, nz) || !(lane == 24u || fb_in_range(a.g, nx, ny, nz))) return;
-  const long long n = fb_ii(a.g, nx, ny, nz);
+  if (!x_in_grid(a.g, nx, ny, nz) || !(lane == 24u || x_in_range(a.g, nx, ny, nz))) return;
+  const unsigned n = x_vi(a.g, nx, ny, nz);
   if (__ldcg(&a.SUMg[n]) != sclock && atomicExch(&a.SUMg[n], sclock) != sclock) x_summarize(a.g, a.cobs, a.MB, a.SUM, nx, ny, nz);
 }
 
@@ -222,8 +251,8 @@ __device__ __forceinline__ void x_refresh_summaries(const XArgs &a, const XShare
   if (lane >= 25u) return;
   int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
   const int nx = x + dx, ny = y + dy, nz = z + dz;
-  if (!fb_in_grid(a.g, nx, ny, nz) || !(lane == 24u || fb_in_range(a.g, nx, ny, nz))) return;
-  const uint4 u = __ldcg(&a.SUM[fb_ii(a.g, nx, ny, nz)]);
+  if (!x_in_grid(a.g, nx, ny, nz) || !(lane == 24u || x_in_range(a.g, nx, ny, nz))) return;
+  const uint4 u = __ldcg(&a.SUM[x_vi(a.g, nx, ny, nz)]);
   if (u.w == FB_UNKNOWN) return;                               // never observed: accepts nothing, its summary never changes
   const unsigned ts = i * 32u + lane;
   bool redo = u.x == ts || u.y == ts;
@@ -255,7 +284,7 @@ __device__ __forceinline__ void x_list_affected(const XArgs &a, const XShared &s
     if (o < nof) {
       int dx, dy, dz; x_unpack_off(sh.off[o], dx, dy, dz);
       const int nx = x + dx, ny = y + dy, nz = z + dz;
-      if (fb_in_grid(g, nx, ny, nz)) w[t] = __ldcg(&a.MB[fb_ii(g, nx, ny, nz)]);
+      if (x_in_grid(g, nx, ny, nz)) w[t] = __ldcg(&a.MB[x_vi(g, nx, ny, nz)]);
     }
   }
   unsigned j[5], st[5];
@@ -291,7 +320,7 @@ __device__ __forceinline__ unsigned long long x_eval(const XArgs &a, const XShar
   if (lane < 24) {
     int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
     qx += dx; qy += dy; qz += dz;
-    valid = fb_in_range(g, qx, qy, qz) && fb_in_grid(g, qx, qy, qz);
+    valid = x_in_range(g, qx, qy, qz) && x_in_grid(g, qx, qy, qz);
   }
   XState st; st.d = 0xffffffffu; st.c = 0; st.ts = XNONE;
   uint32_t snap = 0;
@@ -326,14 +355,14 @@ __device__ __forceinline__ void x_stage(const XArgs &a, const XShared &sh, XNb &
     if (o < X_NOFF) {
       int dx, dy, dz; x_unpack_off(sh.off[o], dx, dy, dz);
       const int nx = x + dx, ny = y + dy, nz = z + dz;
-      if (fb_in_grid(g, nx, ny, nz)) w[t] = __ldcg(&a.MB[fb_ii(g, nx, ny, nz)]);
+      if (x_in_grid(g, nx, ny, nz)) w[t] = __ldcg(&a.MB[x_vi(g, nx, ny, nz)]);
     }
   }
   uint32_t c = 0;
   if (lane < 25u) {
     int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
     const int nx = x + dx, ny = y + dy, nz = z + dz;
-    if (fb_in_grid(g, nx, ny, nz)) c = __ldcg(&a.cobs[fb_ii(g, nx, ny, nz)]);
+    if (x_in_grid(g, nx, ny, nz)) c = __ldcg(&a.cobs[x_vi(g, nx, ny, nz)]);
   }
   __syncwarp();                                                // the previous element's readers are done
 #pragma unroll
@@ -349,7 +378,7 @@ __device__ __forceinline__ XState x_state_nb(const FbGeom &g, const XShared &sh,
   s.c = snap; s.d = (raw & FB_DINF) ? 0xffffffffu : x_dist_of(qx, qy, qz, snap); s.ts = XNONE;
   const unsigned d0 = s.d;
   if (snap == FB_UNKNOWN) return s;                            // never observed: accepts nothing (:382)
-  if (fb_in_range(g, qx, qy, qz)) {                            // pushes only go to voxels inside the update box (:378)
+  if (x_in_range(g, qx, qy, qz)) {                            // pushes only go to voxels inside the update box (:378)
 #pragma unroll 8
     for (int k = 0; k < 24; ++k) {
       const unsigned long long ww = nb.w[sh.slot[lane * 24u + (unsigned)k]];
@@ -378,7 +407,7 @@ __device__ __forceinline__ unsigned long long x_eval_nb(const XArgs &a, const XS
   if (lane < 24) {
     int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
     qx += dx; qy += dy; qz += dz;
-    valid = fb_in_range(g, qx, qy, qz) && fb_in_grid(g, qx, qy, qz);
+    valid = x_in_range(g, qx, qy, qz) && x_in_grid(g, qx, qy, qz);
   }
   XState st; st.d = 0xffffffffu; st.c = 0; st.ts = XNONE;
   uint32_t snap = 0;
@@ -447,15 +476,15 @@ __device__ __forceinline__ uint32_t x_reseed_eval(const XArgs &a, unsigned i, in
   kc = 24u;
   for (int k = 0; k < 24; ++k) {
     const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
-    if (!fb_in_range(g, nx, ny, nz) || !fb_in_grid(g, nx, ny, nz)) continue;
-    const long long nv = fb_ii(g, nx, ny, nz);
+    if (!x_in_range(g, nx, ny, nz) || !x_in_grid(g, nx, ny, nz)) continue;
+    const unsigned nv = x_vi(g, nx, ny, nz);
     const unsigned o = __ldcg(&a.ord[nv]);
     uint32_t c;
     if (o != XNONE) { if (o < i) c = __ldcg(&a.nc[o]); else continue; }
     else c = __ldcg(&a.cobs[nv]) & FB_CODE_MASK;
     if (c >= 2u) {
       int ox, oy, oz; fb_unpack(c, ox, oy, oz);
-      const long long oi = fb_ii(g, ox, oy, oz);
+      const unsigned oi = x_vi(g, ox, oy, oz);
       if ((__ldg(&a.occbits[oi >> 5]) >> (oi & 31)) & 1u) { kc = (unsigned)k; return c; }   // Exist(closest obstacle) (:312), then `break` (:319)
     }
   }
@@ -517,20 +546,20 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
         // by side (three round trips instead of up to 72 one after the other); the round's length is what the sweep costs
         for (unsigned q = gwarp; q < nw; q += gwarps) {
           const unsigned i = r == 1u ? q : __ldcg(&a.W[in][q]);
-          int x, y, z; x_coords(g, __ldcg(&a.deps[i]), x, y, z);
+          int x, y, z; x_coords(a, __ldcg(&a.deps[i]), x, y, z);
           int dx = 0, dy = 0, dz = 0;
           if (lane < 24u) x_unpack_off(sh.dir[lane], dx, dy, dz);
           const int nx = x + dx, ny = y + dy, nz = z + dz;
-          const bool ing = lane < 24u && fb_in_grid(g, nx, ny, nz);
-          const long long nv = ing ? fb_ii(g, nx, ny, nz) : 0;
+          const bool ing = lane < 24u && x_in_grid(g, nx, ny, nz);
+          const unsigned nv = ing ? x_vi(g, nx, ny, nz) : 0u;
           const unsigned o = ing ? __ldcg(&a.ord[nv]) : XNONE;
           uint32_t c = 0;
-          if (ing && fb_in_range(g, nx, ny, nz)) {
+          if (ing && x_in_range(g, nx, ny, nz)) {
             if (o != XNONE) { if (o < i) c = __ldcg(&a.nc[o]); }
             else c = __ldcg(&a.cobs[nv]) & FB_CODE_MASK;
           }
           bool ok = false;
-          if (c >= 2u) { int px, py, pz; fb_unpack(c, px, py, pz); const long long oi = fb_ii(g, px, py, pz); ok = (__ldg(&a.occbits[oi >> 5]) >> (oi & 31)) & 1u; }
+          if (c >= 2u) { int px, py, pz; fb_unpack(c, px, py, pz); const unsigned oi = x_vi(g, px, py, pz); ok = (__ldg(&a.occbits[oi >> 5]) >> (oi & 31)) & 1u; }
           const unsigned vm = __ballot_sync(0xffffffffu, ok);
           const unsigned kc = vm ? (unsigned)(__ffs(vm) - 1) : 24u;                 // first valid neighbour in dirs_ order (:308-321)
           const uint32_t res = vm ? __shfl_sync(0xffffffffu, c, (int)kc) : FB_INF;
@@ -555,7 +584,7 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
       } else
       for (unsigned q = gtid; q < nw; q += gthreads) {
         const unsigned i = r == 1u ? q : __ldcg(&a.W[in][q]);
-        int x, y, z; x_coords(g, __ldcg(&a.deps[i]), x, y, z);
+        int x, y, z; x_coords(a, __ldcg(&a.deps[i]), x, y, z);
         unsigned kc;
         const uint32_t res = x_reseed_eval(a, i, x, y, z, kc);
         const uint32_t was = __ldcg(&a.nc[i]);
@@ -564,8 +593,8 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
         a.nc[i] = res;
         for (int k = 0; k < 24; ++k) {                         // later dependants that look at this one
           const int nx = x + x_dirs[k][0], ny = y + x_dirs[k][1], nz = z + x_dirs[k][2];
-          if (!fb_in_grid(g, nx, ny, nz)) continue;
-          const unsigned o = __ldcg(&a.ord[fb_ii(g, nx, ny, nz)]);
+          if (!x_in_grid(g, nx, ny, nz)) continue;
+          const unsigned o = __ldcg(&a.ord[x_vi(g, nx, ny, nz)]);
           bool push = o != XNONE && o > i;
           if (push) {
             const unsigned so = __ldcg(&a.wstamp[o]);
@@ -644,7 +673,7 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
     unsigned rounds = 0;
     if (big) {
       ++sclock;
-      for (unsigned i = gwarp; i < nE; i += gwarps) { int x, y, z; x_coords(g, __ldcg(&E[i]), x, y, z); x_claim_summaries(a, sh, lane, x, y, z, sclock); }
+      for (unsigned i = gwarp; i < nE; i += gwarps) { int x, y, z; x_coords(a, __ldcg(&E[i]), x, y, z); x_claim_summaries(a, sh, lane, x, y, z, sclock); }
       x_gsync(&ctl->bar, bar_target);
       X_LAP(0);
     }
@@ -663,12 +692,12 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
           for (unsigned q = gwarp; q < nf; q += gwarps) {
             const unsigned i = __ldcg(&a.F[in][q]);
             const uint32_t p = __ldcg(&E[i]);
-            int x, y, z; x_coords(g, p, x, y, z);
+            int x, y, z; x_coords(a, p, x, y, z);
             x_refresh_summaries(a, sh, lane, i, p, x, y, z);
           }
         } else {
           ++sclock;
-          for (unsigned i = gwarp; i < nE; i += gwarps) { int x, y, z; x_coords(g, __ldcg(&E[i]), x, y, z); x_claim_summaries(a, sh, lane, x, y, z, sclock); }
+          for (unsigned i = gwarp; i < nE; i += gwarps) { int x, y, z; x_coords(a, __ldcg(&E[i]), x, y, z); x_claim_summaries(a, sh, lane, x, y, z, sclock); }
         }
         x_gsync(&ctl->bar, bar_target);
       }
@@ -680,13 +709,13 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
         if (q >= nw) {                                         // summaries of the targets of an element that flipped last round
           const unsigned i = __ldcg(&a.F[in][q - nw]);
           const uint32_t p = __ldcg(&E[i]);
-          int x, y, z; x_coords(g, p, x, y, z);
+          int x, y, z; x_coords(a, p, x, y, z);
           x_refresh_summaries(a, sh, lane, i, p, x, y, z);
           continue;
         }
         const unsigned i = r == 1u ? q : __ldcg(&wl[q]);
         const uint32_t p = __ldcg(&E[i]);
-        int x, y, z; x_coords(g, p, x, y, z);
+        int x, y, z; x_coords(a, p, x, y, z);
         if (!use_sum) {                                        // gathering evaluation: everything from one staged round of loads
           x_stage(a, sh, stg, lane, x, y, z);
           const unsigned long long old = stg.w[0], nw2 = x_eval_nb(a, sh, stg, lane, gen, i, x, y, z);
@@ -726,7 +755,7 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
     unsigned wcount = 0, wlive = 0;
     for (unsigned i = lo + wid; i < hi; i += XW) {
       const uint32_t p = __ldcg(&E[i]);
-      int x, y, z; x_coords(g, p, x, y, z);
+      int x, y, z; x_coords(a, p, x, y, z);
       unsigned long long w = 0;
       if (!big) { x_stage(a, sh, stg, lane, x, y, z); w = stg.w[0]; }
       else { if (lane == 0) w = __ldcg(&a.MB[p]); w = __shfl_sync(0xffffffffu, w, 0); }
@@ -735,9 +764,9 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
       if ((kind == X_PUSH && lane < 24) || (kind == X_PULL && lane == 24)) {
         int dx, dy, dz; x_unpack_off(sh.dir[lane], dx, dy, dz);
         const int nx = x + dx, ny = y + dy, nz = z + dz;
-        if (fb_in_grid(g, nx, ny, nz) && (lane == 24 || fb_in_range(g, nx, ny, nz))) {
+        if (x_in_grid(g, nx, ny, nz) && (lane == 24 || x_in_range(g, nx, ny, nz))) {
           const unsigned ts = i * 32u + lane;
-          if (big) win = __ldcg(&a.SUM[fb_ii(g, nx, ny, nz)]).y == ts;
+          if (big) win = __ldcg(&a.SUM[x_vi(g, nx, ny, nz)]).y == ts;
           else {
             uint32_t snap;
             const XState f = x_state_nb(g, sh, stg, lane, nx, ny, nz, XNONE, snap);
@@ -787,12 +816,12 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
       unsigned r = run + x_block_scan(sh, (unsigned)__popc(m), lane, wid, ctot);
       if (m) {                                                 // this thread's element owns slots: records, link times, words of the new entries
         const uint32_t p = __ldcg(&E[i]);
-        int x, y, z; x_coords(g, p, x, y, z);
+        int x, y, z; x_coords(a, p, x, y, z);
         uint32_t me = m;
         while (me) {
           const int k = __ffs(me) - 1; me &= me - 1u;
           int dx, dy, dz; x_unpack_off(sh.dir[k], dx, dy, dz);
-          const uint32_t v = (uint32_t)fb_ii(g, x + dx, y + dy, z + dz);
+          const uint32_t v = (uint32_t)x_vi(g, x + dx, y + dy, z + dz);
           const unsigned ts = i * 32u + (unsigned)k;
           const uint32_t code = big ? __ldcg(&a.SUM[v]).z : __ldcg(&a.slotc[ts]);
           a.cobs[v] = code;
@@ -819,6 +848,14 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
   }
 }
 
+// floor(n / d) == umulhi(n, m) >> s for every n < 2^31: l = ceil(log2 d), m = floor(2^(31+l) / d) + 1 (< 2^32), s = l - 1.
+// (m d = 2^(31+l) + e with 0 < e <= d <= 2^l, so n m / 2^(31+l) exceeds n / d by less than 1 / d.)
+void x_div_make(unsigned d, unsigned &m, unsigned &s) {
+  if (d <= 1u) { m = 0; s = 0; return; }
+  unsigned l = 0; while ((1ull << l) < d) ++l;
+  m = (unsigned)((1ull << (31 + l)) / d + 1ull);
+  s = l - 1u;
+}
 static bool g_off_ready = false;
 cudaError_t fb_xrelax_init() {
   if (g_off_ready) return cudaSuccess;
@@ -854,6 +891,10 @@ cudaError_t fb_xrelax_launch(FbExact *X, const FbGeom &g, uint32_t *cobs, unsign
                              const uint32_t *occbits, unsigned long long ls_deps, unsigned long long *dbg, cudaStream_t s) {
   XArgs a;
   a.deps = deps; a.ndep = ndep; a.ord = ord; a.nc = nc; a.nk = nk; a.occbits = occbits; a.ls_deps = ls_deps;
+  x_div_make((unsigned)g.pz, a.div_pz_m, a.div_pz_s);
+  x_div_make((unsigned)g.gy, a.div_gy_m, a.div_gy_s);
+  if (a.g.max_vec[0] < a.g.min_vec[0] || a.g.max_vec[1] < a.g.min_vec[1] || a.g.max_vec[2] < a.g.min_vec[2])
+    for (int k = 0; k < 3; ++k) a.g.min_vec[k] = a.g.max_vec[k] = 0x3fffffff;      // empty update box: VoxInRange is false everywhere
   a.g = g; a.cobs = cobs; a.MB = X->MB; a.LS = X->LS; a.SUM = X->SUM; a.SUMg = X->SUMg;
   a.E[0] = X->E[0]; a.E[1] = X->E[1]; a.emask = X->emask;
   for (int k = 0; k < 3; ++k) { a.W[k] = X->W[k]; a.F[k] = X->F[k]; }
