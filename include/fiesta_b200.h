@@ -116,7 +116,10 @@ int fiesta_set_occupancy_batch_vox_device(fiesta_map *m, const int *d_vox_xyz, c
  * (raycast.cpp:56-158) and the counter part of SetOccupancy.  xyz: n points (pcl::PointXYZ, 3 floats each) in the
  * sensor frame; T: row-major 4x4 `transform_` (Fiesta.h:415-419); raycast_origin_ = T[:3,3]/T[3,3] (Fiesta.h:420).
  * `fiesta_raycast_frame` takes a HOST pointer; `_device` takes a DEVICE pointer valid on the map's device.  Both return after
- * the frame's counters are complete (the call reads back the frame statistics). */
+ * the frame's counters are complete (the call reads back the frame statistics).
+ * Limits (FIESTA_ERR_LIMIT, nothing is truncated): n <= 524286 points per call (split larger clouds into ordered sub-frames);
+ * 1500 voxels per ray as in the reference (raycast.cpp:127-130); EXACT mode: at most 16383 frames between two
+ * fiesta_update_occupancy calls (observation time stamps are 44 bits per integration epoch). */
 int fiesta_raycast_frame(fiesta_map *m, const float *xyz, int64_t n, const double T[16], const fiesta_raycast_params *p);
 int fiesta_raycast_frame_device(fiesta_map *m, const float *d_xyz, int64_t n, const double T[16],
                                 const fiesta_raycast_params *p);
