@@ -28,6 +28,7 @@
 #include <stdio.h>
 #include "fb_common.cuh"
 #include "fb_exact.h"
+#include "fb_divmagic.h"
 
 #define XT 1024                       // threads per CTA, one CTA per SM
 #define XW (XT / 32)
@@ -215,7 +216,7 @@ struct XArgs {
   const uint32_t *occbits;
   unsigned long long ls_deps;   // link time of dependant 0 (InsertIntoList order, :333)
   unsigned long long *dbg;  // optional per-generation trace {nE, rounds, ns} (FIESTA_DEBUG_X)
-  unsigned div_pz_m, div_pz_s, div_gy_m, div_gy_s;   // n / d = umulhi(n, m) >> s for n < 2^31 (x_div_make); m == 0: d == 1
+  unsigned div_pz_m, div_pz_s, div_gy_m, div_gy_s;   // n / d = umulhi(n, m) >> s for n < 2^31 (fb_div_make, fb_divmagic.h); m == 0: d == 1
 };
 // voxel index -> coordinates: two divisions by run-time constants, as multiply-high + shift
 __device__ __forceinline__ unsigned x_div(unsigned n, unsigned m, unsigned s) { return m ? (__umulhi(n, m) >> s) : n; }
@@ -848,14 +849,6 @@ __global__ void __launch_bounds__(XT, 1) k_x_relax(const XArgs a) {
   }
 }
 
-// floor(n / d) == umulhi(n, m) >> s for every n < 2^31: l = ceil(log2 d), m = floor(2^(31+l) / d) + 1 (< 2^32), s = l - 1.
-// (m d = 2^(31+l) + e with 0 < e <= d <= 2^l, so n m / 2^(31+l) exceeds n / d by less than 1 / d.)
-void x_div_make(unsigned d, unsigned &m, unsigned &s) {
-  if (d <= 1u) { m = 0; s = 0; return; }
-  unsigned l = 0; while ((1ull << l) < d) ++l;
-  m = (unsigned)((1ull << (31 + l)) / d + 1ull);
-  s = l - 1u;
-}
 static bool g_off_ready = false;
 cudaError_t fb_xrelax_init() {
   if (g_off_ready) return cudaSuccess;
@@ -891,11 +884,12 @@ cudaError_t fb_xrelax_launch(FbExact *X, const FbGeom &g, uint32_t *cobs, unsign
                              const uint32_t *occbits, unsigned long long ls_deps, unsigned long long *dbg, cudaStream_t s) {
   XArgs a;
   a.deps = deps; a.ndep = ndep; a.ord = ord; a.nc = nc; a.nk = nk; a.occbits = occbits; a.ls_deps = ls_deps;
-  x_div_make((unsigned)g.pz, a.div_pz_m, a.div_pz_s);
-  x_div_make((unsigned)g.gy, a.div_gy_m, a.div_gy_s);
+  fb_div_make((unsigned)g.pz, a.div_pz_m, a.div_pz_s);
+  fb_div_make((unsigned)g.gy, a.div_gy_m, a.div_gy_s);
+  a.g = g;
   if (a.g.max_vec[0] < a.g.min_vec[0] || a.g.max_vec[1] < a.g.min_vec[1] || a.g.max_vec[2] < a.g.min_vec[2])
-    for (int k = 0; k < 3; ++k) a.g.min_vec[k] = a.g.max_vec[k] = 0x3fffffff;      // empty update box: VoxInRange is false everywhere
-  a.g = g; a.cobs = cobs; a.MB = X->MB; a.LS = X->LS; a.SUM = X->SUM; a.SUMg = X->SUMg;
+    for (int k = 0; k < 3; ++k) a.g.min_vec[k] = a.g.max_vec[k] = 0x3fffffff;      // empty update box: VoxInRange is false everywhere (x_in_range)
+  a.cobs = cobs; a.MB = X->MB; a.LS = X->LS; a.SUM = X->SUM; a.SUMg = X->SUMg;
   a.E[0] = X->E[0]; a.E[1] = X->E[1]; a.emask = X->emask;
   for (int k = 0; k < 3; ++k) { a.W[k] = X->W[k]; a.F[k] = X->F[k]; }
   a.wstamp = X->wstamp; a.slotc = X->slotc; a.ctl = X->d_ctl; a.nE0 = nE0; a.small_max = X->small_max; a.dense_min = X->dense_min; a.dbg = dbg;
